@@ -1,0 +1,386 @@
+"""Host-side mirror of the reference's renderer interface on top of the sm_100a kernels.
+
+``EndoSurfRenderer(render_cfg, net_cfg, device)`` has the member surface the reference trainer uses
+(reference ``src/trainer/trainer_endosurf.py:51,65-68,81,88,130,140,155,230,336,427,453``; class at
+``src/renderer/endosurf.py:14-521``): same constructor, ``forward``/``render_rays`` returning the same 8-key
+dict, ``n_samples``/``n_importance``, ``get_train_params``, ``save_checkpoint``/``load_checkpoint`` with the
+reference's state-dict keys (``net.{l}.bias|weight_g|weight_v``, ``variance``).
+
+Parameters live in ordinary ``nn.Parameter`` objects; the only PyTorch arithmetic on the hot path is folding
+weight norm (``W = g v/||v||``, 1.65 M elements).  Everything per-sample -- encodings, the three MLPs, normals,
+the deformation Jacobian, hierarchical sampling and compositing -- runs in ``libendosurf_b200.so`` through the
+C ABI (``include/endosurf_b200.h``).  There is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+# ------------------------------------------------------------------------------------------------ parameters
+class WNLinear(nn.Module):
+    """Parameters of one weight-normalised linear layer in the reference's (old-API) layout:
+    ``bias``, ``weight_g`` [out,1], ``weight_v`` [out,in] -- registered in that order so that
+    ``parameters()`` / Adam state indices line up with the reference (utils.py:57-58)."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor):
+        super().__init__()
+        self.bias = nn.Parameter(bias.clone())
+        self.weight_g = nn.Parameter(weight.norm(dim=1, keepdim=True).clone())
+        self.weight_v = nn.Parameter(weight.clone())
+
+    def effective_weight(self) -> torch.Tensor:
+        return self.weight_v * (self.weight_g / torch.linalg.norm(self.weight_v, dim=1, keepdim=True))
+
+
+def _default_linear_init(dim_in: int, dim_out: int):
+    lin = nn.Linear(dim_in, dim_out)  # kaiming-uniform(a=sqrt(5)) weight, uniform bias: torch's default
+    return lin.weight.detach(), lin.bias.detach()
+
+
+def _make_mlp(n_layers, hidden, in_dim, out_dim, skips, style, geometric_bias=None):
+    """Layer shapes and initialisation of the reference's builders.
+
+    style "nerf": skip layer takes hidden+in_dim inputs (utils.py:11-60)
+    style "idr" : the layer before a skip emits hidden-in_dim outputs (utils.py:63-111)
+    geometric_bias (float) switches on the SDF sphere initialisation (utils.py:38-56)."""
+    layers = []
+    for l in range(n_layers):
+        if style == "nerf":
+            d0 = in_dim if l == 0 else (hidden + in_dim if l in skips else hidden)
+            d1 = out_dim if l == n_layers - 1 else hidden
+        else:
+            d0 = in_dim if l == 0 else hidden
+            d1 = out_dim if l == n_layers - 1 else (hidden - in_dim if (l + 1) in skips else hidden)
+        w, b = _default_linear_init(d0, d1)
+        if geometric_bias is not None:
+            if l == n_layers - 1:
+                w = torch.empty(d1, d0).normal_(mean=math.sqrt(math.pi) / math.sqrt(d0), std=1e-4)
+                b = torch.full((d1,), -float(geometric_bias))
+            elif l == 0:
+                b = torch.zeros(d1)
+                w = torch.zeros(d1, d0)
+                w[:, :3].normal_(0.0, math.sqrt(2) / math.sqrt(d1))
+            elif l in skips:
+                b = torch.zeros(d1)
+                w = torch.empty(d1, d0).normal_(0.0, math.sqrt(2) / math.sqrt(d1))
+                w[:, -(in_dim - 3):] = 0.0
+            else:
+                b = torch.zeros(d1)
+                w = torch.empty(d1, d0).normal_(0.0, math.sqrt(2) / math.sqrt(d1))
+        layers.append(WNLinear(w, b))
+    return nn.ModuleList(layers)
+
+
+def _enc_dim(cfg) -> int:
+    if cfg["enc_type"] != "frequency":
+        raise NotImplementedError("endosurf_b200 kernels implement the frequency encoder only")
+    return cfg["input_dim"] * (1 + 2 * cfg["multires"])
+
+
+class _Net(nn.Module):
+    def __init__(self, net: nn.ModuleList):
+        super().__init__()
+        self.net = net
+
+
+class _Variance(nn.Module):
+    def __init__(self, init_val):
+        super().__init__()
+        self.variance = nn.Parameter(torch.tensor(float(init_val)))
+
+
+class EndoSurfNet(nn.Module):
+    """Parameter container with the reference's module/parameter names (endosurf.py:524-568)."""
+
+    def __init__(self, net_cfg: dict):
+        super().__init__()
+        self.bound = net_cfg["bound"]
+        self.use_deform = bool(net_cfg["use_deform"])
+        if self.use_deform:
+            c = net_cfg["deform_network"]
+            in_dim = _enc_dim(c["enc_pos_cfg"]) + _enc_dim(c["enc_time_cfg"])
+            self.deform_network = _Net(_make_mlp(c["n_layers"], c["hidden_dim"], in_dim, c["out_dim"],
+                                                 list(c["skips"]), "idr"))
+        c = net_cfg["sdf_network"]
+        self.sdf_network = _Net(_make_mlp(c["n_layers"], c["hidden_dim"], _enc_dim(c["enc_pos_cfg"]), c["out_dim"],
+                                          list(c["skips"]), "nerf",
+                                          geometric_bias=c.get("geometric_init_bias", 0.8)
+                                          if c.get("geometric_init", True) else None))
+        c = net_cfg["color_network"]
+        in_dim = _enc_dim(c["enc_pos_cfg"]) + 3 + _enc_dim(c["enc_dir_cfg"]) + c["feat_dim"]
+        self.color_network = _Net(_make_mlp(c["n_layers"], c["hidden_dim"], in_dim, c["out_dim"], list(c["skips"]),
+                                            "nerf"))
+        self.deviation_network = _Variance(net_cfg["deviation_network"]["init_val"])
+
+    def get_train_params(self) -> Dict[str, List[nn.Parameter]]:
+        p = {}
+        if self.use_deform:
+            p["deform_network"] = list(self.deform_network.parameters())
+        p["sdf_network"] = list(self.sdf_network.parameters())
+        p["color_network"] = list(self.color_network.parameters())
+        p["deviation_network"] = list(self.deviation_network.parameters())
+        return p
+
+    def save_checkpoint(self):
+        ck = {}
+        if self.use_deform:
+            ck["deform_network"] = self.deform_network.state_dict()
+        ck["sdf_network"] = self.sdf_network.state_dict()
+        ck["color_network"] = self.color_network.state_dict()
+        ck["deviation_network"] = self.deviation_network.state_dict()
+        return ck
+
+    def load_checkpoints(self, ckpt):
+        if self.use_deform:
+            self.deform_network.load_state_dict(ckpt["deform_network"])
+        self.sdf_network.load_state_dict(ckpt["sdf_network"])
+        self.color_network.load_state_dict(ckpt["color_network"])
+        self.deviation_network.load_state_dict(ckpt["deviation_network"])
+
+
+def _net_config_struct(net_cfg: dict, precision_terms: int) -> _lib.EsNetConfig:
+    s, c = net_cfg["sdf_network"], net_cfg["color_network"]
+    d = net_cfg.get("deform_network", None) if net_cfg["use_deform"] else None
+    nets = [n for n in (d, s, c) if n is not None]
+    n_layers = {n["n_layers"] for n in nets}
+    hidden = {n["hidden_dim"] for n in nets}
+    skips = {tuple(n["skips"]) for n in nets}
+    if len(n_layers) != 1 or len(hidden) != 1 or len(skips) != 1 or len(next(iter(skips))) > 1:
+        raise NotImplementedError("endosurf_b200 kernels need the three networks to share n_layers/hidden_dim and "
+                                  "a single skip layer (every shipped reference config does)")
+    if s["out_dim"] != 257 or c["feat_dim"] != 256 or c["out_dim"] != 3 or (d is not None and d["out_dim"] != 3):
+        raise NotImplementedError("unsupported output widths")
+    sk = next(iter(skips))
+    return _lib.EsNetConfig(
+        use_deform=int(bool(net_cfg["use_deform"])), n_layers=n_layers.pop(), skip_layer=sk[0] if sk else -1,
+        hidden_dim=hidden.pop(),
+        multires_deform_pos=d["enc_pos_cfg"]["multires"] if d else 6,
+        multires_deform_time=d["enc_time_cfg"]["multires"] if d else 6,
+        multires_sdf_pos=s["enc_pos_cfg"]["multires"],
+        multires_color_pos=c["enc_pos_cfg"]["multires"], multires_color_dir=c["enc_dir_cfg"]["multires"],
+        precision_terms=precision_terms)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class EndoSurfRenderer(nn.Module):
+    """Drop-in for the reference ``EndoSurfRenderer`` (endosurf.py:14-132) backed by the CUDA library."""
+
+    def __init__(self, render_cfg, net_cfg, device="cuda", precision_terms: int = 3):
+        super().__init__()
+        self.render_cfg = render_cfg
+        self.net_cfg = net_cfg
+        self.device = device
+        self.dtype = torch.get_default_dtype()
+        if self.dtype != torch.float32:
+            raise NotImplementedError("endosurf_b200 computes in fp32 storage (bf16x3 tensor-core products)")
+        self.model = EndoSurfNet(net_cfg).to(device)
+        self.anneal_end = render_cfg["anneal_end"]
+        self.n_samples = render_cfg["n_samples"]
+        self.perturb = render_cfg["perturb"]
+        self.n_importance = render_cfg["n_importance"]
+        self.important_begin_iter = render_cfg["important_begin_iter"]
+        self.up_sample_steps = render_cfg["up_sample_steps"]
+        self.net_chunk = render_cfg["net_chunk"]  # accepted for compatibility; the fused kernels need no chunking
+        self._cfg_struct = _net_config_struct(net_cfg, precision_terms)
+        self._ctx = None
+        self._packed_version = None
+        self._consts = {}
+
+    # ------------------------------------------------------------------ reference surface
+    def get_train_params(self):
+        return self.model.get_train_params()
+
+    def load_checkpoint(self, ckpt):
+        self.model.load_checkpoints(ckpt)
+        self._packed_version = None
+
+    def save_checkpoint(self):
+        return self.model.save_checkpoint()
+
+    def get_cos_anneal_ratio(self, iter_step):
+        """endosurf.py:215-219"""
+        if self.anneal_end == 0.0:
+            return 1.0
+        return float(np.min([1.0, iter_step / self.anneal_end]))
+
+    def forward(self, rays, **kwargs):
+        return self.render_rays(rays, **kwargs)
+
+    # ------------------------------------------------------------------ library plumbing
+    def _context(self):
+        if self._ctx is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("endosurf_b200 needs a CUDA sm_100 device; there is no CPU fallback")
+            lib = _lib.load()
+            dev = torch.device(self.device)
+            torch.cuda.set_device(dev if dev.index is not None else torch.cuda.current_device())
+            ctx = C.c_void_p()
+            rc = lib.es_create(C.byref(ctx), C.byref(self._cfg_struct))
+            if rc != 0:
+                raise _lib.EsError(f"es_create failed: {_lib.ES_E.get(rc, rc)}")
+            self._ctx = ctx
+        return self._ctx
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None) is not None:
+                _lib.load().es_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _params_version(self):
+        return tuple(p._version for p in self.model.parameters()) + tuple(p.data_ptr() for p in self.model.parameters())
+
+    def _sync_weights(self):
+        """Fold weight norm (PyTorch, differentiable plumbing) and repack when any parameter changed."""
+        ver = self._params_version()
+        if ver == self._packed_version:
+            return
+        lib, ctx = _lib.load(), self._context()
+        nets = []
+        if self.model.use_deform:
+            nets.append((0, self.model.deform_network))
+        nets += [(1, self.model.sdf_network), (2, self.model.color_network)]
+        keep = []
+        with torch.no_grad():
+            for net_id, mod in nets:
+                ws = [l.effective_weight().contiguous() for l in mod.net]
+                bs = [l.bias.detach().contiguous() for l in mod.net]
+                keep += ws + bs
+                wp = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+                bp = (C.c_void_p * len(bs))(*[b.data_ptr() for b in bs])
+                _lib.check(ctx, lib.es_load_network(ctx, net_id, wp, bp, self._stream()), "es_load_network")
+        self._keepalive = keep  # folded tensors stay alive until the pack kernels have been enqueued and run
+        self._packed_version = ver
+
+    def _const(self, key, fn):
+        if key not in self._consts:
+            self._consts[key] = fn()
+        return self._consts[key]
+
+    def sync_check(self):
+        """Synchronise and raise if any kernel tripped its device-side watchdog (tests / debugging)."""
+        lib, ctx = _lib.load(), self._context()
+        _lib.check(ctx, lib.es_sync_check(ctx, self._stream()), "es_sync_check")
+
+    def launch_count(self) -> int:
+        return int(_lib.load().es_launch_count(self._context()))
+
+    # ------------------------------------------------------------------ network queries (EndoSurfNet surface)
+    def sdf_from_observed_space(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """EndoSurfNet.get_sdf_from_observed_space (endosurf.py:570-579); no grad."""
+        self._sync_weights()
+        lib, ctx = _lib.load(), self._context()
+        x = x.detach().reshape(-1, 3).contiguous().float()
+        n = x.shape[0]
+        t = t.detach().reshape(-1).contiguous().float()
+        t_div = 1 if t.numel() == n else n
+        out = torch.empty(n, 1, device=x.device, dtype=torch.float32)
+        _lib.check(ctx, lib.es_sdf_query(ctx, _ptr(x), _ptr(t), t_div, 1, n, _ptr(out), self._stream()),
+                   "es_sdf_query")
+        return out
+
+    def point_forward(self, x, d, t, want_feat=False) -> Dict[str, torch.Tensor]:
+        """EndoSurfNet.forward + the gradient queries (endosurf.py:581-689) on explicit points; no grad.
+        Returns x_c, jac, sdf, g_c, g_o, rgb (and feat)."""
+        self._sync_weights()
+        lib, ctx = _lib.load(), self._context()
+        x = x.detach().reshape(-1, 3).contiguous().float()
+        d = d.detach().reshape(-1, 3).contiguous().float()
+        n = x.shape[0]
+        t = t.detach().reshape(-1).contiguous().float()
+        t_div = 1 if t.numel() == n else n
+        dev = x.device
+        o = dict(x_c=torch.empty(n, 3, device=dev), jac=torch.empty(n, 3, 3, device=dev),
+                 sdf=torch.empty(n, 1, device=dev), g_c=torch.empty(n, 3, device=dev),
+                 rgb=torch.empty(n, 3, device=dev))
+        if want_feat:
+            o["feat"] = torch.empty(n, 256, device=dev)
+        _lib.check(ctx, lib.es_point_forward(ctx, _ptr(x), _ptr(t), t_div, 1, _ptr(d), 1, 3, n, _ptr(o["x_c"]),
+                                             _ptr(o["jac"]), _ptr(o["sdf"]), _ptr(o["g_c"]), _ptr(o.get("feat")),
+                                             _ptr(o["rgb"]), self._stream()), "es_point_forward")
+        o["g_o"] = torch.einsum("nij,ni->nj", o["jac"], o["g_c"])
+        return o
+
+    def up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, inv_s):
+        """endosurf.py:221-266"""
+        lib, ctx = _lib.load(), self._context()
+        R, n = z_vals.shape
+        rays = torch.cat([rays_o, rays_d, torch.zeros(R, 3, device=z_vals.device)], -1).contiguous().float()
+        u = torch.linspace(0.0 + 0.5 / n_importance, 1.0 - 0.5 / n_importance, steps=n_importance,
+                           device=z_vals.device)
+        out = torch.empty(R, n_importance, device=z_vals.device)
+        _lib.check(ctx, lib.es_up_sample(ctx, _ptr(rays), R, _ptr(z_vals.contiguous().float()),
+                                         _ptr(sdf.reshape(R, n).contiguous().float()), n, n_importance, _ptr(u),
+                                         float(inv_s), _ptr(out), self._stream()), "es_up_sample")
+        return out
+
+    # ------------------------------------------------------------------ the hot path
+    def render_rays(self, rays, iter_step=0, perturb_overwrite=None, eval=False, z_vals_override=None,
+                    return_extras=False, **kwargs):
+        """EndoSurfRenderer.render_rays (endosurf.py:60-132): rays [R,9] -> the reference's 8-key dict."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+            raise NotImplementedError(
+                "the differentiable (training) render_rays path of endosurf_b200 is not built yet; call under "
+                "torch.no_grad() for the forward path (DESIGN.md, 'what comes next')")
+        self._sync_weights()
+        lib, ctx = _lib.load(), self._context()
+        rays = rays.detach().contiguous().float()
+        dev = rays.device
+        R = rays.shape[0]
+        ns, ni = int(self.n_samples), int(self.n_importance)
+        perturb = self.perturb if perturb_overwrite is None else perturb_overwrite
+        do_up = bool(iter_step >= self.important_begin_iter and ni > 0)
+        M = ns + (ni if do_up else 0)
+        t_vals = self._const(("t", ns, dev), lambda: torch.linspace(0.0, 1.0, ns, device=dev))
+        steps = int(self.up_sample_steps)
+        u_vals = None
+        if do_up:
+            k = ni // steps
+            u_vals = self._const(("u", k, dev),
+                                 lambda: torch.linspace(0.0 + 0.5 / k, 1.0 - 0.5 / k, steps=k, device=dev))
+        t_rand = None
+        if perturb and z_vals_override is None:
+            t_rand = (torch.rand([R, 1], device=dev) - 0.5).reshape(-1).contiguous()  # endosurf.py:81
+        zo = None
+        if z_vals_override is not None:
+            zo = z_vals_override.detach().contiguous().float()
+        out = {
+            "color_map": torch.empty(R, 3, device=dev), "depth_map": torch.empty(R, 1, device=dev),
+            "gradients_o": torch.empty(R, M, 3, device=dev), "gradient_o_error": torch.empty((), device=dev),
+            "weights": torch.empty(R, M, device=dev), "weight_max": torch.empty(R, 1, device=dev),
+            "cdf": torch.empty(R, M, device=dev), "s_val": torch.empty(R, 1, device=dev),
+        }
+        extras = {}
+        if return_extras:
+            extras = {"z_vals": torch.empty(R, M, device=dev), "sdf": torch.empty(R, M, device=dev),
+                      "sampled_color": torch.empty(R, M, 3, device=dev)}
+        if zo is not None and zo.shape != (R, M):
+            raise ValueError(f"z_vals_override must be [{R},{M}] for this render config, got {tuple(zo.shape)}")
+        prm = _lib.EsRenderParams(
+            n_samples=ns, n_importance=ni, up_sample_steps=steps, do_upsample=int(do_up),
+            cos_anneal_ratio=float(self.get_cos_anneal_ratio(iter_step)),
+            variance=self.model.deviation_network.variance.data_ptr(), t_vals=t_vals.data_ptr(),
+            u_vals=u_vals.data_ptr() if u_vals is not None else None,
+            t_rand=t_rand.data_ptr() if t_rand is not None else None,
+            z_override=zo.data_ptr() if zo is not None else None)
+        o = _lib.EsRenderOut(**{k: v.data_ptr() for k, v in {**out, **extras}.items()})
+        rc = lib.es_render_rays(ctx, _ptr(rays), R, C.byref(prm), C.byref(o), self._stream())
+        _lib.check(ctx, rc, "es_render_rays")
+        out.update(extras)
+        return out

@@ -1,0 +1,226 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the golden vectors
+generated from the reference and against the oracle on the same seeded inputs.
+
+Tolerances (north_star: 1e-4 relative fp32): per-ray integrals and smooth per-point quantities are checked as
+max|a-b| / max|b| <= 1e-4.  Quantities that contain derivatives of the ReLU deformation network (Jacobian, g_o,
+gradients_o) are discontinuous at ReLU kinks, so they use the kink-tolerant check of conftest.assert_close."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz, load_cfg, load_ckpt, assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _renderer(cfg, ckpt, ns=None, ni=None, use_deform=True, terms=3):
+    from endosurf_b200 import EndoSurfRenderer
+    rc = copy.deepcopy(cfg["render"])
+    if ns is not None:
+        rc.update(n_samples=ns, n_importance=ni)
+    rc["perturb"] = False
+    nc = copy.deepcopy(cfg["net"])
+    nc["use_deform"] = use_deform
+    r = EndoSurfRenderer(rc, nc, device="cuda", precision_terms=terms)
+    r.load_checkpoint({k: v for k, v in ckpt.items() if use_deform or k != "deform_network"})
+    r.eval()
+    return r
+
+
+def _bf16_bits(x):
+    return x.to(torch.bfloat16).view(torch.int16)
+
+
+def test_umma_probe_layout():
+    """One 128x256x64 bf16 GEMM through the kernels' smem descriptors / bulk TMA / TMEM read-back."""
+    import ctypes as C
+    from endosurf_b200 import _lib
+    cfg = load_cfg()
+    r = _renderer(cfg, load_ckpt())
+    lib, ctx = _lib.load(), r._context()
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(128, 64, generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn(256, 64, generator=g).to(torch.bfloat16).cuda()
+    ref = a.float() @ b.float().t()
+    results = {}
+    for name, (al, asb, bl, bs) in {"default": (0, 0, 0, 0), "swapped": (128, 2048, 128, 4096)}.items():
+        d = torch.zeros(128, 256, device="cuda")
+        rc = lib.es_umma_probe(ctx, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(d.data_ptr()),
+                               al, asb, bl, bs, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        results[name] = rel_err(d, ref)
+    r.sync_check()
+    assert results["default"] < 1e-5, f"UMMA descriptor convention wrong: {results}"
+
+
+def test_sdf_query_stage(cfg, ckpt):
+    s = load_npz("stage_points.npz")
+    r = _renderer(cfg, ckpt)
+    x, t = torch.from_numpy(s["x"]).cuda(), torch.from_numpy(s["t"]).cuda()
+    sdf = r.sdf_from_observed_space(x, t)
+    r.sync_check()
+    assert_close("sdf", sdf, s["sdf"], TOL)
+
+
+def test_point_forward_stage(cfg, ckpt):
+    s = load_npz("stage_points.npz")
+    r = _renderer(cfg, ckpt)
+    x, d, t = (torch.from_numpy(s[k]).cuda() for k in "xdt")
+    o = r.point_forward(x, d, t, want_feat=True)
+    r.sync_check()
+    for k in ["x_c", "sdf", "feat", "g_c", "rgb"]:
+        assert_close(k, o[k], s[k], TOL)
+    for k in ["jac", "g_o"]:
+        assert_close(k, o[k], s[k], TOL, kink_tol=5e-3)
+
+
+def test_point_forward_ragged_sizes(cfg, ckpt):
+    """tile tails: 1 point, a non-multiple of the 32/128-point tiles, and more tiles than SMs would not matter."""
+    s = load_npz("stage_points.npz")
+    r = _renderer(cfg, ckpt)
+    for n in (1, 31, 33, 129, 192):
+        x, d, t = (torch.from_numpy(s[k][:n]).cuda() for k in "xdt")
+        o = r.point_forward(x, d, t)
+        r.sync_check()
+        assert_close(f"sdf[{n}]", o["sdf"], s["sdf"][:n], TOL)
+        assert_close(f"rgb[{n}]", o["rgb"], s["rgb"][:n], TOL)
+        assert_close(f"g_c[{n}]", o["g_c"], s["g_c"][:n], TOL)
+        q = r.sdf_from_observed_space(x, t)
+        assert_close(f"sdfq[{n}]", q, s["sdf"][:n], TOL)
+
+
+def test_up_sample_trace(cfg, ckpt):
+    g = load_npz("render_r32_s32_i32_it25k.npz")
+    r = _renderer(cfg, ckpt, 32, 32)
+    rays = torch.from_numpy(g["rays"]).cuda()
+    for i in range(4):
+        z, sdf, new_z = (torch.from_numpy(g[f"up{i}_{k}"]).cuda() for k in ("z", "sdf", "new_z"))
+        out = r.up_sample(rays[:, :3], rays[:, 3:6], z, sdf, 8, 64 * 2 ** i)
+        r.sync_check()
+        assert_close(f"new_z step {i}", out, new_z, 2e-5)
+
+
+CASES = [("r48_s64_i64_it0", True), ("r48_s64_i64_it50k", True), ("r32_s32_i32_it25k", True),
+         ("r32_s64_i0_it0", True), ("r32_nodeform_s32_i32", False)]
+
+
+@pytest.mark.parametrize("tag,use_deform", CASES)
+def test_render_core_fixed_z(cfg, ckpt, tag, use_deform):
+    """render_core on the reference's z_vals: per-sample tensors are comparable (no resampling in between)."""
+    g = load_npz(f"render_{tag}.npz")
+    r = _renderer(cfg, ckpt, int(g["n_samples"]), int(g["n_importance"]), use_deform)
+    rays = torch.from_numpy(g["rays"]).cuda()
+    z = torch.from_numpy(g["z_vals"]).cuda()
+    with torch.no_grad():
+        o = r.render_rays(rays, iter_step=int(g["iter_step"]), perturb_overwrite=False, z_vals_override=z,
+                          return_extras=True)
+    r.sync_check()
+    for k in ["color_map", "depth_map", "weights", "cdf"]:
+        assert_close(k, o[k], g["core/" + k], TOL)
+    assert_close("gradient_o_error", o["gradient_o_error"], g["core/gradient_o_error"], TOL)
+    assert_close("gradients_o", o["gradients_o"], g["core/gradients_o"], TOL, kink_tol=5e-3)
+    assert_close("sdf", o["sdf"], g["sdf"], TOL)
+    assert_close("sampled_color", o["sampled_color"], g["sampled_color"], TOL)
+
+
+@pytest.mark.parametrize("tag,use_deform", CASES)
+def test_render_rays_end_to_end(cfg, ckpt, tag, use_deform):
+    """Full render_rays incl. hierarchical sampling: per-ray integrals (SURVEY 7 hard part 2, BASELINE parity gate)."""
+    g = load_npz(f"render_{tag}.npz")
+    r = _renderer(cfg, ckpt, int(g["n_samples"]), int(g["n_importance"]), use_deform)
+    rays = torch.from_numpy(g["rays"]).cuda()
+    with torch.no_grad():
+        o = r.render_rays(rays, iter_step=int(g["iter_step"]), perturb_overwrite=False, return_extras=True)
+    r.sync_check()
+    assert set(["color_map", "depth_map", "gradients_o", "gradient_o_error", "weights", "weight_max", "cdf",
+                "s_val"]) <= set(o.keys())
+    assert_close("z_vals", o["z_vals"], g["z_vals"], 1e-3)   # resampled positions (discontinuous; loose)
+    for k in ["color_map", "depth_map", "s_val", "gradient_o_error"]:
+        assert_close(k, o[k], g[k], TOL)
+    assert_close("weight_max", o["weight_max"], g["weight_max"], 5e-4)
+
+
+def test_render_rays_vs_oracle_larger(cfg, ckpt):
+    """256 seeded rays, 64+64 samples, against the oracle run on the host CPU of the GPU box."""
+    from oracle import endosurf_oracle as orc
+    rc = copy.deepcopy(cfg["render"])
+    rc.update(n_samples=64, n_importance=64, perturb=False)
+    rays = orc.synthetic_rays(256, frame=33, seed=21)
+    net = orc.OracleNet(ckpt, cfg["net"])
+    with torch.no_grad():
+        ref = orc.render_rays(net, rc, rays, iter_step=50000, perturb_overwrite=False)
+    r = _renderer(cfg, ckpt, 64, 64)
+    with torch.no_grad():
+        o = r.render_rays(rays.cuda(), iter_step=50000, perturb_overwrite=False)
+        oc = r.render_rays(rays.cuda(), iter_step=50000, z_vals_override=ref["z_vals"].cuda(), return_extras=True)
+    r.sync_check()
+    for k in ["color_map", "depth_map", "gradient_o_error", "s_val"]:
+        assert_close(k, o[k], ref[k], TOL)
+    for k in ["color_map", "depth_map", "weights", "cdf"]:
+        assert_close("core/" + k, oc[k], ref[k], TOL)
+    assert_close("core/gradients_o", oc["gradients_o"], ref["gradients_o"], TOL, kink_tol=5e-3)
+
+
+def test_full_size_properties(cfg, ckpt):
+    """BASELINE config 2 size (4096 rays, 64+64): size-independent invariants of NeuS compositing."""
+    from oracle import endosurf_oracle as orc
+    r = _renderer(cfg, ckpt, 64, 64)
+    rays = orc.synthetic_rays(4096, frame=7, seed=5).cuda()
+    with torch.no_grad():
+        o = r.render_rays(rays, iter_step=50000, perturb_overwrite=False, return_extras=True)
+        o2 = r.render_rays(rays, iter_step=50000, perturb_overwrite=False, return_extras=True)
+    r.sync_check()
+    for k, v in o.items():
+        assert torch.isfinite(v).all(), k
+    w = o["weights"]
+    assert (w >= 0).all() and (w.sum(-1) <= 1.0 + 1e-4).all()
+    assert (o["cdf"] >= 0).all() and (o["cdf"] <= 1).all()
+    z = o["z_vals"]
+    assert (z[:, 1:] >= z[:, :-1]).all(), "z_vals must be sorted"
+    assert torch.allclose(o["weight_max"][:, 0], w.max(-1)[0])
+    assert (o["color_map"] >= 0).all() and (o["color_map"] <= 1 + 1e-4).all()
+    # colour is a convex-ish combination: color_map == sum_i w_i c_i
+    assert_close("color recomposed", (o["sampled_color"] * w[..., None]).sum(1), o["color_map"], 1e-5)
+    # deterministic: same inputs -> bit-identical outputs
+    for k in o:
+        assert torch.equal(o[k], o2[k]), k
+    # a permutation of the rays permutes the per-ray outputs (rays are independent)
+    perm = torch.randperm(4096, generator=torch.Generator().manual_seed(0)).cuda()
+    with torch.no_grad():
+        op = r.render_rays(rays[perm], iter_step=50000, perturb_overwrite=False)
+    assert_close("perm color", op["color_map"], o["color_map"][perm], 1e-6)
+    assert_close("perm depth", op["depth_map"], o["depth_map"][perm], 1e-6)
+
+
+def test_edge_cases(cfg, ckpt):
+    from oracle import endosurf_oracle as orc
+    r = _renderer(cfg, ckpt, 32, 32)
+    # empty batch
+    with torch.no_grad():
+        o = r.render_rays(torch.zeros(0, 9, device="cuda"), iter_step=0)
+    assert o["color_map"].shape == (0, 3)
+    # single ray and rays that miss the unit sphere (near = far: degenerate sections)
+    rays = orc.synthetic_rays(3, frame=1, seed=2)
+    rays[1, 3:6] = torch.tensor([0.9, 0.1, 0.42])
+    rays[1, 3:6] /= rays[1, 3:6].norm()
+    net = orc.OracleNet(ckpt, cfg["net"])
+    rc = copy.deepcopy(cfg["render"])
+    rc.update(n_samples=32, n_importance=32, perturb=False)
+    with torch.no_grad():
+        ref = orc.render_rays(net, rc, rays, iter_step=1000, perturb_overwrite=False)
+        o = r.render_rays(rays.cuda(), iter_step=1000, perturb_overwrite=False)
+    r.sync_check()
+    for k in ["color_map", "depth_map"]:
+        assert torch.isfinite(o[k]).all()
+        assert_close(k, o[k], ref[k], TOL)
+
+
+def test_training_path_is_loud(cfg, ckpt):
+    r = _renderer(cfg, ckpt, 32, 32)
+    r.train()
+    with pytest.raises(NotImplementedError):
+        r.render_rays(torch.zeros(4, 9, device="cuda"), iter_step=0)
