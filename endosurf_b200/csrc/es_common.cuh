@@ -3,7 +3,7 @@
 // Everything is inline PTX; no CUTLASS dependency.
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace es {
@@ -115,13 +115,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version for sm_100
   return d;                             // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
-// kind::f16, A/B = bf16 K-major, D = fp32, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+// kind::f16, A/B = fp16 (format code 0) K-major, D = fp32 (c_format 1), M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -136,12 +136,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// ------------------------------------------------------------------ bf16 hi/lo split
-// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi)  (both round-to-nearest-even).
+// ------------------------------------------------------------------ fp16 hi/lo split
+// x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi) (round-to-nearest-even): 22 mantissa bits, i.e. a relative
+// representation error of 2^-22, 16x tighter than a bf16 pair for the same three MMAs (hi*hi + hi*lo + lo*hi).
+// Products of two fp16 values are exact in the fp32 accumulator.  Range: |x| must stay below 65504 (activations,
+// tangents and weights of these weight-normalised 256-wide MLPs are O(1..100)); tiny values lose nothing that
+// matters because the error is absolute (fp16 subnormal spacing 6e-8).
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  float2 hf = __bfloat1622float2(h);
-  __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  __half2 h = __floats2half2_rn(a, b);
+  float2 hf = __half22float2(h);
+  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
 }

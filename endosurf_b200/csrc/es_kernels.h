@@ -37,14 +37,14 @@ cudaError_t launch_mlp_chain(int chain, bool tangent, bool use_deform, const Cha
                              int n_sms, cudaStream_t stream);
 int mlp_chain_smem_bytes();
 
-// ---- tcgen05 layout self-test (es_probe.cu): one 128x256x64 bf16 GEMM through the same descriptors
-cudaError_t launch_umma_probe(const uint16_t* a_bf16 /*[128][64]*/, const uint16_t* b_bf16 /*[256][64]*/,
+// ---- tcgen05 layout self-test (es_probe.cu): one 128x256x64 fp16 GEMM through the same descriptors
+cudaError_t launch_umma_probe(const uint16_t* a_f16 /*[128][64]*/, const uint16_t* b_f16 /*[256][64]*/,
                               float* d /*[128][256]*/, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int* err,
                               cudaStream_t stream);
 
 // ---- weight packing (es_pack.cu)
 // Gathers columns of an fp32 [n_out, n_in] matrix into the kernel's K order (colmap[k] = source column or -1),
-// scales, zero-pads rows to 256 and K to 32*n_sub, splits into bf16 hi/lo and writes 16 KiB units
+// scales, zero-pads rows to 256 and K to 32*n_sub, splits into fp16 hi/lo and writes 16 KiB units
 // [hi(sub0), lo(sub0), hi(sub1), lo(sub1), ...] in the canonical no-swizzle K-major UMMA layout.
 cudaError_t launch_pack_layer(const float* w, int n_out, int n_in, const int* colmap_dev, int k_total, float scale,
                               uint8_t* units_out, cudaStream_t stream);

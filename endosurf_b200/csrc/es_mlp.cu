@@ -1,10 +1,10 @@
 // Fused per-point MLP chains of the EndoSurf renderer on sm_100a tensor cores.
 //
 // One persistent CTA per SM walks 128-row tiles through a chain of 256-wide layers:
-//   warp 0      : TMA producer   - streams packed bf16 weight units (16 KiB, cp.async.bulk) L2 -> smem ring
-//   warp 1      : MMA issuer     - tcgen05.mma (M128 N256 K16, bf16 x bf16 -> fp32 in TMEM), 3-term hi/lo split
+//   warp 0      : TMA producer   - streams packed fp16 weight units (16 KiB, cp.async.bulk) L2 -> smem ring
+//   warp 1      : MMA issuer     - tcgen05.mma (M128 N256 K16, fp16 x fp16 -> fp32 in TMEM), 3-term hi/lo split
 //   warps 2..9  : epilogue       - tcgen05.ld the accumulator, bias + activation (+ forward-mode tangents),
-//                                  split to bf16 hi/lo and write the next layer's A operand into the smem ring;
+//                                  split to fp16 hi/lo and write the next layer's A operand into the smem ring;
 //                                  also evaluates positional encodings, the 3-wide output layers and the outputs.
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the MMA of layer l+1 starts on K chunk 0 while
 // the epilogue is still converting chunks 1..3 of layer l.  Activations never touch HBM.
@@ -128,7 +128,7 @@ __device__ __forceinline__ void encode_half(float (&v)[32], const float (&pos)[3
   });
 }
 
-// split v[32] into bf16 hi/lo and store as sub-block `half` of A ring slot `slot_base` for row `row`
+// split v[32] into fp16 hi/lo and store as sub-block `half` of A ring slot `slot_base` for row `row`
 __device__ __forceinline__ void store_a_half(uint8_t* slot_base, int row, int half, const float (&v)[32]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -321,7 +321,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
   } else if (warp == 1) {
     // ============================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TILE_ROWS, HID);
+      constexpr uint32_t idesc = make_idesc_f16(TILE_ROWS, HID);
       uint32_t wc = 0, ac = 0, g = 0;
       const uint32_t a_base = smem_u32(smem + SM_A_OFF);
       const uint32_t w_base = smem_u32(smem + SM_W_OFF);
@@ -348,10 +348,10 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
                 for (int ks = 0; ks < 2; ++ks) {
                   const uint64_t bd = make_smem_desc(w_st + ks * 2 * B_LBO, B_LBO, B_SBO);
                   const uint32_t a_off = (sb * 4 + ks * 2) * A_LBO;
-                  umma_bf16_ss(d_tmem, make_smem_desc(a_slot + a_off, A_LBO, A_SBO), bd, idesc, accum);
+                  umma_f16_ss(d_tmem, make_smem_desc(a_slot + a_off, A_LBO, A_SBO), bd, idesc, accum);
                   accum = 1;
                   if (prog.n_terms == 3)
-                    umma_bf16_ss(d_tmem, make_smem_desc(a_slot + SLOT_HALF_BYTES + a_off, A_LBO, A_SBO), bd, idesc,
+                    umma_f16_ss(d_tmem, make_smem_desc(a_slot + SLOT_HALF_BYTES + a_off, A_LBO, A_SBO), bd, idesc,
                                  1);
                 }
                 umma_commit(&bars.w_empty[st]);
@@ -367,7 +367,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
                 for (int ks = 0; ks < 2; ++ks) {
                   const uint64_t bd = make_smem_desc(w_st + ks * 2 * B_LBO, B_LBO, B_SBO);
                   const uint32_t a_off = (sb * 4 + ks * 2) * A_LBO;
-                  umma_bf16_ss(d_tmem, make_smem_desc(a_slot + a_off, A_LBO, A_SBO), bd, idesc, 1);
+                  umma_f16_ss(d_tmem, make_smem_desc(a_slot + a_off, A_LBO, A_SBO), bd, idesc, 1);
                 }
                 umma_commit(&bars.w_empty[st]);
                 ++wc;

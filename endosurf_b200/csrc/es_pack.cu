@@ -1,4 +1,4 @@
-// Weight packing: effective fp32 weights (weight-norm already folded, reference utils.py:57-58) -> bf16 hi/lo UMMA
+// Weight packing: effective fp32 weights (weight-norm already folded, reference utils.py:57-58) -> fp16 hi/lo UMMA
 // operand units in the exact order the TMA producer streams them.  Runs once per parameter update (1.65 M elements).
 #include "es_common.cuh"
 #include "es_program.h"

@@ -1,10 +1,11 @@
-// tcgen05 layout self-test: D[128,256] = A[128,64] * B[256,64]^T with bf16 operands staged in shared memory in the
+// tcgen05 layout self-test: D[128,256] = A[128,64] * B[256,64]^T with fp16 operands staged in shared memory in the
 // same canonical no-swizzle K-major layout, the same shared-memory descriptors, the same bulk-TMA weight copy and
 // the same TMEM read-back as the fused MLP kernel.  The descriptor strides are runtime arguments so a test can
 // confirm the (LBO, SBO) convention on real hardware.
 #include "es_common.cuh"
 #include "es_program.h"
 #include "es_kernels.h"
+#include <cstdlib>
 
 namespace es {
 
@@ -13,7 +14,7 @@ constexpr int PROBE_B_BYTES = 256 * 64 * 2;  // 32 KiB
 
 __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const uint16_t* __restrict__ a, const uint8_t* __restrict__ b_packed, float* __restrict__ d,
-                  int a_lbo, int a_sbo, int b_lbo, int b_sbo, int* err) {
+                  int a_lbo, int a_sbo, int b_lbo, int b_sbo, int* err, int mode) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sa = smem;
   uint8_t* sb = smem + PROBE_A_BYTES;
@@ -43,28 +44,28 @@ umma_probe_kernel(const uint16_t* __restrict__ a, const uint8_t* __restrict__ b_
     fence_proxy_async_smem();
   }
   // B: already packed in global memory as two 16 KiB units [kgroup][n][8]; bulk TMA like the producer warp
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && (mode & 1)) {
     mbar_arrive_expect_tx(bar_w, PROBE_B_BYTES);
     tma_bulk_g2s(sb, b_packed, UNIT_BYTES, bar_w);
     tma_bulk_g2s(sb + UNIT_BYTES, b_packed + UNIT_BYTES, UNIT_BYTES, bar_w);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_wait(bar_w, 0, err, 900);
+  if (threadIdx.x == 0 && (mode & 2)) {
+    if (mode & 1) mbar_wait(bar_w, 0, err, 900);
     tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(128, 256);
+    const uint32_t idesc = make_idesc_f16(128, 256);
     for (int ks = 0; ks < 4; ++ks) {
       // unit u = ks/2 holds k-groups 4u..4u+3 at stride B_LBO inside the unit
       const uint32_t b_addr = smem_u32(sb) + (ks / 2) * UNIT_BYTES + (ks % 2) * 2 * B_LBO;
       const uint32_t a_addr = smem_u32(sa) + ks * 2 * A_LBO;
-      umma_bf16_ss(tmem_base, make_smem_desc(a_addr, a_lbo, a_sbo), make_smem_desc(b_addr, b_lbo, b_sbo), idesc,
+      umma_f16_ss(tmem_base, make_smem_desc(a_addr, a_lbo, a_sbo), make_smem_desc(b_addr, b_lbo, b_sbo), idesc,
                    ks > 0);
     }
     umma_commit(bar_d);
   }
-  mbar_wait(bar_d, 0, err, 901);
+  if (mode & 2) mbar_wait(bar_d, 0, err, 901);
   tc_fence_after();
-  for (int blk = 0; blk < 8; ++blk) {
+  for (int blk = 0; blk < 8 && (mode & 4); ++blk) {
     float v[32];
     tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + blk * 32, v);
     tmem_ld_wait();
@@ -86,6 +87,8 @@ __global__ void probe_pack_b(const uint16_t* __restrict__ b, uint8_t* __restrict
 
 cudaError_t launch_umma_probe(const uint16_t* a, const uint16_t* b, float* d, int a_lbo, int a_sbo, int b_lbo,
                               int b_sbo, int* err, cudaStream_t stream) {
+  const char* m = getenv("ES_PROBE_MODE");
+  const int mode = m ? atoi(m) : 7;
   uint8_t* packed = nullptr;
   cudaError_t e = cudaMallocAsync(&packed, PROBE_B_BYTES, stream);
   if (e != cudaSuccess) return e;
@@ -93,7 +96,7 @@ cudaError_t launch_umma_probe(const uint16_t* a, const uint16_t* b, float* d, in
   const int smem = PROBE_A_BYTES + PROBE_B_BYTES + 64;
   e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  umma_probe_kernel<<<1, 128, smem, stream>>>(a, packed, d, a_lbo, a_sbo, b_lbo, b_sbo, err);
+  umma_probe_kernel<<<1, 128, smem, stream>>>(a, packed, d, a_lbo, a_sbo, b_lbo, b_sbo, err, mode);
   e = cudaGetLastError();
   cudaFreeAsync(packed, stream);
   return e;

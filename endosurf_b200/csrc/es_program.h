@@ -13,7 +13,7 @@ constexpr int SUB_K = 32;          // K extent of one weight unit
 constexpr int SLOT_HALF_BYTES = TILE_ROWS * CHUNK_K * 2;  // 16 KiB: hi or lo plane of a slot
 constexpr int SLOT_BYTES = 2 * SLOT_HALF_BYTES;           // 32 KiB
 constexpr int NSLOT = 4;
-constexpr int UNIT_BYTES = HID * SUB_K * 2;               // 16 KiB: 256 x 32 bf16 (hi or lo)
+constexpr int UNIT_BYTES = HID * SUB_K * 2;               // 16 KiB: 256 x 32 fp16 (hi or lo)
 constexpr int NSTAGE = 4;
 // canonical no-swizzle K-major layout: [k-group of 8][row][8 elements]
 constexpr int A_LBO = TILE_ROWS * 16;  // 2048  bytes between K core matrices
@@ -50,7 +50,7 @@ struct LayerProg {
 struct ChainProg {
   int32_t n_layers;
   int32_t units_per_tile;  // 16 KiB weight units streamed per tile (hi and lo counted separately)
-  int32_t n_terms;         // 3: bf16x3 split (fp32 parity); 1: single bf16 pass
+  int32_t n_terms;         // 3: fp16x3 split (fp32 parity); 1: single fp16 pass
   int32_t post_op;
   LayerProg layer[MAXL];
   const uint8_t* w_units;  // packed weight units, consumption order

@@ -183,7 +183,7 @@ class EndoSurfRenderer(nn.Module):
         self.device = device
         self.dtype = torch.get_default_dtype()
         if self.dtype != torch.float32:
-            raise NotImplementedError("endosurf_b200 computes in fp32 storage (bf16x3 tensor-core products)")
+            raise NotImplementedError("endosurf_b200 computes in fp32 storage (fp16 hi/lo split tensor-core products)")
         self.model = EndoSurfNet(net_cfg).to(device)
         self.anneal_end = render_cfg["anneal_end"]
         self.n_samples = render_cfg["n_samples"]

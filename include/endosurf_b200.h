@@ -36,7 +36,7 @@ typedef struct es_net_config {
   int32_t multires_deform_pos, multires_deform_time; /* 6, 6 */
   int32_t multires_sdf_pos;                          /* 6 */
   int32_t multires_color_pos, multires_color_dir;    /* 10, 4 */
-  int32_t precision_terms;  /* 3 = bf16x3 split (fp32 parity, default); 1 = single bf16 pass */
+  int32_t precision_terms;  /* 3 = fp16x3 hi/lo split (fp32 parity, default); 1 = single fp16 pass */
 } es_net_config;
 
 enum { ES_NET_DEFORM = 0, ES_NET_SDF = 1, ES_NET_COLOR = 2 };
@@ -50,7 +50,7 @@ int es_num_sms(const es_ctx* ctx);
 
 /* Upload one network's EFFECTIVE weights W_l = g_l * v_l / ||v_l|| (reference utils.py:57-58, folded by the caller)
  * and biases: w[l] -> [out_l, in_l] row-major, b[l] -> [out_l], l = 0..n_layers-1, in the reference's own layout
- * (DeformNetwork/SDFNetwork/ColorNetwork.net[l], endosurf.py:713,762,817).  Packs them into bf16 hi/lo UMMA units. */
+ * (DeformNetwork/SDFNetwork/ColorNetwork.net[l], endosurf.py:713,762,817).  Packs them into fp16 hi/lo UMMA units. */
 int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* const* b, void* stream);
 
 /* EndoSurfNet.get_sdf_from_observed_space (endosurf.py:570-579).
@@ -112,7 +112,7 @@ int64_t es_launch_count(const es_ctx* ctx);
  * 64 chunk columns reads for network `net` (or -1 for padding).  src: 1 deform enc, 2 sdf enc, 3 colour A, 4 colour B. */
 int es_chunk_colmap(const es_ctx* ctx, int net, int src, int32_t* out64);
 
-/* tcgen05 self-test: d[128,256] = a[128,64] (bf16 bits) * b[256,64]^T (bf16 bits) through the same shared-memory
+/* tcgen05 self-test: d[128,256] = a[128,64] (fp16 bits) * b[256,64]^T (fp16 bits) through the same shared-memory
  * descriptors / TMA / TMEM path as the fused kernels.  lbo/sbo <= 0 selects the built-in strides. */
 int es_umma_probe(es_ctx* ctx, const uint16_t* a, const uint16_t* b, float* d, int32_t a_lbo, int32_t a_sbo,
                   int32_t b_lbo, int32_t b_sbo, void* stream);

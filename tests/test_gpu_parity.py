@@ -35,26 +35,25 @@ def _bf16_bits(x):
 
 
 def test_umma_probe_layout():
-    """One 128x256x64 bf16 GEMM through the kernels' smem descriptors / bulk TMA / TMEM read-back."""
+    """One 128x256x64 fp16 GEMM through the kernels' smem descriptors / bulk TMA / TMEM read-back."""
     import ctypes as C
     from endosurf_b200 import _lib
     cfg = load_cfg()
     r = _renderer(cfg, load_ckpt())
     lib, ctx = _lib.load(), r._context()
     g = torch.Generator().manual_seed(0)
-    a = torch.randn(128, 64, generator=g).to(torch.bfloat16).cuda()
-    b = torch.randn(256, 64, generator=g).to(torch.bfloat16).cuda()
+    a = torch.randn(128, 64, generator=g).to(torch.float16).cuda()
+    b = torch.randn(256, 64, generator=g).to(torch.float16).cuda()
     ref = a.float() @ b.float().t()
-    results = {}
-    for name, (al, asb, bl, bs) in {"default": (0, 0, 0, 0), "swapped": (128, 2048, 128, 4096)}.items():
-        d = torch.zeros(128, 256, device="cuda")
-        rc = lib.es_umma_probe(ctx, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(d.data_ptr()),
-                               al, asb, bl, bs, None)
-        assert rc == 0
-        torch.cuda.synchronize()
-        results[name] = rel_err(d, ref)
+    d = torch.zeros(128, 256, device="cuda")
+    rc = lib.es_umma_probe(ctx, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(d.data_ptr()),
+                           0, 0, 0, 0, None)
+    assert rc == 0
+    torch.cuda.synchronize()
     r.sync_check()
-    assert results["default"] < 1e-5, f"UMMA descriptor convention wrong: {results}"
+    # (confirmed on B200: LBO = byte stride between the two K core matrices, SBO = stride between 8-row groups;
+    #  the swapped convention reads out of the shared-memory window and faults)
+    assert rel_err(d, ref) < 1e-5, "UMMA descriptor convention wrong"
 
 
 def test_sdf_query_stage(cfg, ckpt):

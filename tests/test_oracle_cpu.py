@@ -98,19 +98,22 @@ def test_kernel_model_exact_matches_reference(cfg, ckpt):
         assert_close(k, o[k], s[k], 5e-6, kink_tol=5e-3)
 
 
-def test_kernel_model_bf16x3_within_parity_budget(cfg, ckpt):
-    """3-term bf16 split with fp32 accumulation stays well inside the 1e-4 budget per point;
-    a single bf16 pass does not (the reason precision_terms defaults to 3)."""
+def test_kernel_model_split_precision(cfg, ckpt):
+    """fp16 hi/lo split (3 MMAs, fp32 accumulate) sits at the fp32 noise floor per point; a bf16 pair is ~10x worse
+    (measured on the B200: per-sample NeuS weights off by 1.9e-4) and a single pass is useless for parity --
+    the reason precision_terms defaults to 3 and the operands are fp16, not bf16."""
     s = load_npz("stage_points.npz")
     x, d, t = (torch.from_numpy(s[k]) for k in "xdt")
-    o3 = km.point_pipeline(ckpt, cfg["net"], x, d, t, km.mm_bf16x3)
+    o3 = km.point_pipeline(ckpt, cfg["net"], x, d, t, km.mm_f16x3)
     for k in ["x_c", "jac", "sdf", "feat", "g_c", "g_o", "rgb"]:
-        assert_close(k, o3[k], s[k], 5e-5, kink_tol=5e-3)
-    o1 = km.point_pipeline(ckpt, cfg["net"], x, d, t, km.mm_bf16x1)
-    assert rel_err(o1["g_c"], s["g_c"]) > 1e-3
+        assert_close(k, o3[k], s[k], 8e-6, kink_tol=5e-3)
+    ob = km.point_pipeline(ckpt, cfg["net"], x, d, t, km.mm_bf16x3)
+    assert rel_err(ob["sdf"], s["sdf"]) > 3 * rel_err(o3["sdf"], s["sdf"])
+    o1 = km.point_pipeline(ckpt, cfg["net"], x, d, t, km.mm_f16x1)
+    assert rel_err(o1["g_c"], s["g_c"]) > 1e-4
 
 
-def test_kernel_model_render_core_bf16x3(cfg, ckpt):
+def test_kernel_model_render_core_f16x3(cfg, ckpt):
     g = load_npz("render_r32_s32_i32_it25k.npz")
     rays = torch.from_numpy(g["rays"])
     z = torch.from_numpy(g["z_vals"])
@@ -122,9 +125,9 @@ def test_kernel_model_render_core_bf16x3(cfg, ckpt):
     pts = rays[:, None, :3] + dz[:, None, :] * mid[..., None]
     dirs = rays[:, None, 3:6].expand(R, M, 3)
     tt = rays[:, None, 8:9].expand(R, M, 1)
-    o = km.point_pipeline(ckpt, cfg["net"], pts.reshape(-1, 3), dirs.reshape(-1, 3), tt.reshape(-1, 1), km.mm_bf16x3)
+    o = km.point_pipeline(ckpt, cfg["net"], pts.reshape(-1, 3), dirs.reshape(-1, 3), tt.reshape(-1, 1), km.mm_f16x3)
     inv_s = float(torch.exp(ckpt["deviation_network"]["variance"] * 10.0).clip(1e-6, 1e6))
     c = km.composite(o["sdf"].reshape(R, M), o["g_o"].reshape(R, M, 3), o["rgb"].reshape(R, M, 3), rays[:, 3:6],
                      pts, z, 2.0 / ns, inv_s, orc.cos_anneal_ratio(int(g["iter_step"]), 50000))
     for k in ["color_map", "depth_map", "weights", "cdf", "gradient_o_error"]:
-        assert_close(k, c[k], g["core/" + k], 1e-4)
+        assert_close(k, c[k], g["core/" + k], 2e-5)
