@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the render_rays hot path (BASELINE.json: rays/sec, 512x512 frames, 64+64 samples).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1          # reference algorithm on the host CPU cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                     # one rank per GPU, weak scaling over ray batches
+
+A step is one render_rays call on a batch of `--rays` synthetic rays of one 512x512 frame (configs[1] of
+BASELINE.json: 4096 rays, 64 coarse + 64 fine samples, 4 up-sampling steps, 9x256 networks, fp32 parity mode).
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for what every key means.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- algorithmic work per unit (1 MAC = 2 FLOP) -----------------------------------------------------
+D_MAC, S_MAC, C_MAC = 459_520, 544_512, 638_208  # deform / sdf / colour MLP, MAC per point
+
+
+def flops_per_ray(ns, ni, steps):
+    m = ns + ni
+    u = ns + (steps - 1) * ni // steps if ni > 0 else 0
+    return 2.0 * (u * (D_MAC + S_MAC) + m * (4 * D_MAC + 2 * S_MAC + C_MAC))
+
+
+NET_CFG = {
+    "bound": 1.0, "use_deform": True,
+    "deform_network": {"enc_pos_cfg": {"enc_type": "frequency", "input_dim": 3, "multires": 6},
+                       "enc_time_cfg": {"enc_type": "frequency", "input_dim": 1, "multires": 6},
+                       "n_layers": 9, "hidden_dim": 256, "skips": [4], "out_dim": 3},
+    "sdf_network": {"enc_pos_cfg": {"enc_type": "frequency", "input_dim": 3, "multires": 6},
+                    "n_layers": 9, "hidden_dim": 256, "skips": [4], "out_dim": 257, "geometric_init": True,
+                    "geometric_init_bias": 0.8},
+    "color_network": {"enc_pos_cfg": {"enc_type": "frequency", "input_dim": 3, "multires": 10},
+                      "enc_dir_cfg": {"enc_type": "frequency", "input_dim": 3, "multires": 4},
+                      "n_layers": 9, "hidden_dim": 256, "skips": [4], "feat_dim": 256, "out_dim": 3},
+    "deviation_network": {"init_val": 0.3},
+}  # == net: of configs/endosurf/baseline/base_pull.yml:40-82
+RENDER_CFG = {"type": "endosurf", "net_chunk": 80000, "anneal_end": 50000, "n_samples": 64, "n_importance": 64,
+              "important_begin_iter": 0, "up_sample_steps": 4, "perturb": True}
+ITER_STEP = 50000
+
+
+def make_rays(n_rays, frame, hw=512, n_frames=60, seed=0):
+    """Pinhole rays from o=(0,0,-1.5) over a 512x512 image (focal 1.2*W), one frame per batch, time=frame/59."""
+    g = torch.Generator().manual_seed(seed + 7919 * frame)
+    pix = torch.randint(0, hw * hw, (n_rays,), generator=g)
+    u = (pix % hw).float() + 0.5
+    v = (pix // hw).float() + 0.5
+    f = 1.2 * hw
+    d = torch.stack([(u - hw / 2) / f, (v - hw / 2) / f, torch.ones_like(u)], -1)
+    d = d / d.norm(dim=-1, keepdim=True)
+    o = torch.tensor([0.0, 0.0, -1.5]).expand(n_rays, 3)
+    return torch.cat([o, d, torch.zeros(n_rays, 2), torch.full((n_rays, 1), frame / (n_frames - 1))], -1).contiguous()
+
+
+def seeded_state(renderer_module):
+    """Random-init weights of the reference architecture: geometric SDF init + seeded noise (a deforming surface)."""
+    g = torch.Generator().manual_seed(1234)
+    with torch.no_grad():
+        for n, p in renderer_module.named_parameters():
+            s = 0.004 if "sdf_network" in n else 0.02
+            p.add_(s * torch.randn(p.shape, generator=g).to(p.device))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.stop_flag, self.idx = [], False, gpu_index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j.get("bf16_tflops_sustained", j.get("bf16_tflops"))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
+
+
+def oracle_cpu_rays_per_s(n_rays, repeats, threads):
+    """Reference algorithm (oracle port; the reference is pure Python/PyTorch and cannot travel) on the host CPU."""
+    from oracle import endosurf_oracle as orc  # checker / baseline only
+    from endosurf_b200 import EndoSurfNet
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = EndoSurfNet(NET_CFG)
+    seeded_state(model)
+    ck = {k: {kk: vv.detach() for kk, vv in sd.items()} for k, sd in model.save_checkpoint().items()}
+    net = orc.OracleNet(ck, NET_CFG)
+    rc = copy.deepcopy(RENDER_CFG)
+    times = []
+    for i in range(repeats + 1):
+        rays = make_rays(n_rays, frame=i)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.render_rays(net, rc, rays, iter_step=ITER_STEP)
+        times.append(time.perf_counter() - t0)
+    t = float(np.median(times[1:])) if repeats > 0 else times[0]
+    return n_rays / t, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.ref_rays
+    from oracle import endosurf_oracle as orc  # noqa
+    v, _ = oracle_cpu_rays_per_s(n, 0, threads)  # warm the allocator / thread pool
+    times = []
+    for _ in range(max(args.warmup - 1, 0)):
+        oracle_cpu_rays_per_s(n, 0, threads)
+    for _ in range(args.steps):
+        _, t = oracle_cpu_rays_per_s(n, 0, threads)
+        times.append(t)
+    ms = 1e3 * float(np.mean(times))
+    val = n / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.rays),
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} rays x (64+64 samples, 4 up-sampling steps) per step, forward, torch "
+                                   f"{torch.__version__} CPU fp32, {threads} threads"},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+METRIC = "render_rays forward rays/sec (512x512 frames, 64+64 samples)"
+
+
+def workload_config(n_rays, note=None):
+    c = {"workload": f"render_rays forward, {n_rays}-ray batch of one 512x512 frame, 64 coarse + 64 fine samples, "
+                     "4 up-sampling steps, deform+sdf+colour 9x256 MLPs, fp32-parity (fp16 hi/lo x3) tensor-core mode",
+         "rays_per_step_per_gpu": n_rays, "n_samples": 64, "n_importance": 64, "up_sample_steps": 4,
+         "parallelism": "rays sharded per rank, no data-path collective (forward)",
+         "l2_policy": "per-step working set (>= 1 GiB of per-point scratch) exceeds the 126 MB L2; ray batches rotate"}
+    if note:
+        c["note"] = note
+    return c
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from endosurf_b200 import EndoSurfRenderer
+
+    torch.manual_seed(0)
+    r = EndoSurfRenderer(copy.deepcopy(RENDER_CFG), NET_CFG, device=f"cuda:{local}")
+    seeded_state(r.model)
+    r.eval()
+    R, K, W = args.rays, args.steps, args.warmup
+    n_batches = min(K + W, 16)
+    host = [make_rays(R, frame=(rank * 17 + i) % 60, seed=rank).pin_memory() for i in range(n_batches)]
+    devb = [h.to(dev) for h in host]
+    out_c = torch.empty(R, 3).pin_memory()
+    out_d = torch.empty(R, 1).pin_memory()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(W):
+            r.render_rays(devb[i % n_batches], iter_step=ITER_STEP)
+        r.sync_check()
+        # ---------------- device-resident timing (value) + per-kernel roofline
+        r.profile(True)
+        launches0 = r.launch_count()
+        clocks = ClockSampler(local)
+        sync_all()
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            r.render_rays(devb[(W + i) % n_batches], iter_step=ITER_STEP)
+        e1.record()
+        sync_all()
+        ms_total = e0.elapsed_time(e1)
+        clk = clocks.stop() if rank == 0 else None
+        launches = r.launch_count() - launches0
+        prof = r.profile_read()
+        r.profile(False)
+        # ---------------- end to end: pinned host rays in, colour + depth back to the host, every step
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(K):
+            rays = host[(W + i) % n_batches].to(dev, non_blocking=True)
+            o = r.render_rays(rays, iter_step=ITER_STEP)
+            out_c.copy_(o["color_map"], non_blocking=True)
+            out_d.copy_(o["depth_map"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        sync_all()
+        e2e_s = time.perf_counter() - t0
+        r.sync_check()
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t[0].item() / K
+    e2e_ms_step = t[1].item() / K
+    if rank == 0:
+        value = world * R / (ms_step * 1e-3)
+        e2e = world * R / (e2e_ms_step * 1e-3)
+        peak, peak_src = measured_peak_tflops()
+        g = prof["geometry_chain"]
+        pts_per_launch = g["points"] / max(g["launches"], 1)
+        alg_flops_launch = pts_per_launch * 2.0 * (4 * D_MAC + 2 * S_MAC)
+        ms_launch = g["ms"] / max(g["launches"], 1)
+        achieved = alg_flops_launch / (ms_launch * 1e-3) / 1e12 if ms_launch > 0 else 0.0
+        kern_ms = {k: v["ms"] / K for k, v in prof.items()}
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp16 hi/lo x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
+            "config": workload_config(R),
+            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": R * 9 * 4, "d2h_bytes_per_step": R * 4 * 4,
+                    "ms_per_step": e2e_ms_step},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "mlp_chain_kernel<CHAIN_SDF,TANGENT> (geometry chain)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "algorithmic_flops_per_launch": alg_flops_launch, "points_per_launch": pts_per_launch,
+                         "ms_per_launch": ms_launch,
+                         "note": "algorithmic = 2*(4D+2S) FLOP/point (SURVEY 8d); the kernel issues 3 fp16 MMAs per "
+                                 "product (hi/lo split) and 4D+4S+feat (forward-mode normals), i.e. ~3.6x the "
+                                 "algorithmic MMA work, so frac <= ~0.28 by construction",
+                         "kernel_ms_per_step": kern_ms,
+                         "step_algorithmic_tflops": value / world * flops_per_ray(64, 64, 4) / 1e12},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, tt = oracle_cpu_rays_per_s(args.ref_rays, 1, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                                    "sample": f"{args.ref_rays} rays of the same workload, forward, oracle port of "
+                                              f"the reference (PyTorch {torch.__version__} CPU fp32), {tt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=4096, help="rays per step per GPU (BASELINE configs[1])")
+    ap.add_argument("--ref-rays", type=int, default=128, help="bounded CPU sample per step for the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

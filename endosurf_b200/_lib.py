@@ -32,6 +32,10 @@ class EsRenderOut(C.Structure):
         "z_vals", "sdf", "sampled_color")]
 
 
+class EsProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * 3), ("launches", C.c_int64 * 3), ("points", C.c_int64 * 3)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "es_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(EsNetConfig)]),
@@ -50,6 +54,8 @@ EXPORTS = {
     "es_render_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(EsRenderParams),
                                  C.POINTER(EsRenderOut), C.c_void_p]),
     "es_launch_count": (C.c_int64, [C.c_void_p]),
+    "es_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "es_profile_read": (C.c_int, [C.c_void_p, C.POINTER(EsProfile), C.c_void_p]),
     "es_chunk_colmap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "es_umma_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_void_p]),

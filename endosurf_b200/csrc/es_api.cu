@@ -58,6 +58,14 @@ struct es_ctx {
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
   ChainProg prog_sdfq{}, prog_geom{}, prog_color{};
+  // optional per-kernel timing (es_profile_*)
+  bool profiling = false;
+  struct Timed {
+    int kind;
+    long long points;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<Timed> timed;
 };
 
 namespace {
@@ -439,6 +447,23 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
   return 0;
 }
 
+static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const ChainProg& prog, const ChainIO& io,
+                       cudaStream_t stream) {
+  es_ctx::Timed t{kind, io.n_points, nullptr, nullptr};
+  if (ctx->profiling) {
+    CU(cudaEventCreate(&t.e0));
+    CU(cudaEventCreate(&t.e1));
+    CU(cudaEventRecord(t.e0, stream));
+  }
+  CU(launch_mlp_chain(chain, tangent, ctx->cfg.use_deform != 0, prog, io, ctx->n_sms, stream));
+  ++ctx->launches;
+  if (ctx->profiling) {
+    CU(cudaEventRecord(t.e1, stream));
+    ctx->timed.push_back(t);
+  }
+  return 0;
+}
+
 static int check_loaded(es_ctx* ctx, bool need_color) {
   if (!ctx->loaded[ES_NET_DEFORM] || !ctx->loaded[ES_NET_SDF] || (need_color && !ctx->loaded[ES_NET_COLOR]))
     return fail(ctx, ES_E_NOWEIGHTS, "es_load_network has not been called for every network");
@@ -459,10 +484,7 @@ int es_sdf_query(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int
   io.t_div = t ? t_div : 1;
   io.t_stride = t ? t_stride : 0;
   io.out_sdf = sdf_out;
-  CU(launch_mlp_chain(CHAIN_SDF, false, ctx->cfg.use_deform != 0, ctx->prog_sdfq, io, ctx->n_sms,
-                      static_cast<cudaStream_t>(stream)));
-  ++ctx->launches;
-  return 0;
+  return timed_chain(ctx, 2, CHAIN_SDF, false, ctx->prog_sdfq, io, static_cast<cudaStream_t>(stream));
 }
 
 int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride, const float* dirs,
@@ -505,8 +527,7 @@ int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div,
   io.out_sdf = sdf;
   io.out_gc = g_c;
   io.out_feat = feat;
-  CU(launch_mlp_chain(CHAIN_SDF, true, ctx->cfg.use_deform != 0, ctx->prog_geom, io, ctx->n_sms, stream));
-  ++ctx->launches;
+  if (int r = timed_chain(ctx, 0, CHAIN_SDF, true, ctx->prog_geom, io, stream)) return r;
   if (!ctx->cfg.use_deform)  // canonical = observed space (endosurf.py:576-577)
     CU(cudaMemcpyAsync(x_c, x, static_cast<size_t>(n) * 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   if (!ctx->cfg.use_deform && jac) {
@@ -529,8 +550,7 @@ int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div,
     ic.dir_stride = dir_stride;
     ic.feat = feat;
     ic.out_rgb = rgb;
-    CU(launch_mlp_chain(CHAIN_COLOR, false, true, ctx->prog_color, ic, ctx->n_sms, stream));
-    ++ctx->launches;
+    if (int r = timed_chain(ctx, 1, CHAIN_COLOR, false, ctx->prog_color, ic, stream)) return r;
   }
   return 0;
 }
@@ -667,6 +687,29 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
   }
   CU(launch_eikonal_reduce(eik, n_rays, out->gradient_o_error, stream));
   ++ctx->launches;
+  return 0;
+}
+
+int es_profile_enable(es_ctx* ctx, int32_t on) {
+  if (!ctx) return ES_E_BADARG;
+  ctx->profiling = on != 0;
+  return 0;
+}
+
+int es_profile_read(es_ctx* ctx, es_profile* out, void* stream) {
+  if (!ctx || !out) return ES_E_BADARG;
+  CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  std::memset(out, 0, sizeof(*out));
+  for (auto& t : ctx->timed) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, t.e0, t.e1));
+    out->ms[t.kind] += ms;
+    out->launches[t.kind] += 1;
+    out->points[t.kind] += t.points;
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  ctx->timed.clear();
   return 0;
 }
 

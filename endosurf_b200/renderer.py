@@ -278,6 +278,19 @@ class EndoSurfRenderer(nn.Module):
         lib, ctx = _lib.load(), self._context()
         _lib.check(ctx, lib.es_sync_check(ctx, self._stream()), "es_sync_check")
 
+    def profile(self, on: bool):
+        """Bracket every fused MLP-chain launch with CUDA events (bench.py roofline)."""
+        lib, ctx = _lib.load(), self._context()
+        _lib.check(ctx, lib.es_profile_enable(ctx, int(on)), "es_profile_enable")
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        lib, ctx = _lib.load(), self._context()
+        p = _lib.EsProfile()
+        _lib.check(ctx, lib.es_profile_read(ctx, C.byref(p), self._stream()), "es_profile_read")
+        names = ["geometry_chain", "color_chain", "sdf_query_chain"]
+        return {n: {"ms": p.ms[i], "launches": int(p.launches[i]), "points": int(p.points[i])}
+                for i, n in enumerate(names)}
+
     def launch_count(self) -> int:
         return int(_lib.load().es_launch_count(self._context()))
 

@@ -105,6 +105,18 @@ typedef struct es_render_out { /* the reference's 8-key dict (endosurf.py:123-13
 int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_render_params* p,
                    const es_render_out* out, void* stream);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled every fused MLP-chain launch is bracketed with
+ * CUDA events on the launching stream.  es_profile_read synchronises the stream, returns the accumulated durations
+ * since the last read and resets them.  kind: 0 = geometry chain (deform+sdf with tangent rows and feature layer),
+ * 1 = colour chain, 2 = sdf query chain. */
+typedef struct es_profile {
+  double ms[3];
+  int64_t launches[3];
+  int64_t points[3];
+} es_profile;
+int es_profile_enable(es_ctx* ctx, int32_t on);
+int es_profile_read(es_ctx* ctx, es_profile* out, void* stream);
+
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t es_launch_count(const es_ctx* ctx);
 
