@@ -56,6 +56,8 @@ EXPORTS = {
     "es_launch_count": (C.c_int64, [C.c_void_p]),
     "es_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "es_profile_read": (C.c_int, [C.c_void_p, C.POINTER(EsProfile), C.c_void_p]),
+    "es_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "es_mma_bench": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int64)]),
     "es_chunk_colmap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "es_umma_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_void_p]),

@@ -19,6 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 SOURCES = {
     "es_mlp.cu": [],
     "es_probe.cu": [],
+    "es_mmabench.cu": [],
     "es_pack.cu": [],
     "es_rays.cu": ["-fmad=false"],
     "es_api.cu": [],

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -60,6 +61,7 @@ struct es_ctx {
   ChainProg prog_sdfq{}, prog_geom{}, prog_color{};
   // optional per-kernel timing (es_profile_*)
   bool profiling = false;
+  long long* trace_dev = nullptr;  // debug pipeline trace buffer (es_debug_trace)
   struct Timed {
     int kind;
     long long points;
@@ -450,12 +452,18 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
 static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const ChainProg& prog, const ChainIO& io,
                        cudaStream_t stream) {
   es_ctx::Timed t{kind, io.n_points, nullptr, nullptr};
+  ChainIO io2 = io;
+  io2.trace = ctx->trace_dev;
+  {
+    const char* f = getenv("ES_DEBUG_FLAGS");
+    io2.debug_flags = f ? atoi(f) : 0;
+  }
   if (ctx->profiling) {
     CU(cudaEventCreate(&t.e0));
     CU(cudaEventCreate(&t.e1));
     CU(cudaEventRecord(t.e0, stream));
   }
-  CU(launch_mlp_chain(chain, tangent, ctx->cfg.use_deform != 0, prog, io, ctx->n_sms, stream));
+  CU(launch_mlp_chain(chain, tangent, ctx->cfg.use_deform != 0, prog, io2, ctx->n_sms, stream));
   ++ctx->launches;
   if (ctx->profiling) {
     CU(cudaEventRecord(t.e1, stream));
@@ -710,6 +718,37 @@ int es_profile_read(es_ctx* ctx, es_profile* out, void* stream) {
     cudaEventDestroy(t.e1);
   }
   ctx->timed.clear();
+  return 0;
+}
+
+int es_debug_trace(es_ctx* ctx, int64_t* host_out, int64_t capacity_pairs) {
+  // host_out == NULL: arm the trace (next chain launches record into it); else copy out [count, (clock, code)...]
+  if (!ctx) return ES_E_BADARG;
+  const size_t bytes = (1 + 2 * 8000) * sizeof(long long);
+  if (!host_out) {
+    if (!ctx->trace_dev) CU(cudaMalloc(&ctx->trace_dev, bytes));
+    CU(cudaMemset(ctx->trace_dev, 0, bytes));
+    return 0;
+  }
+  if (!ctx->trace_dev) return ES_E_BADARG;
+  CU(cudaDeviceSynchronize());
+  size_t n = std::min<size_t>(bytes, (1 + 2 * static_cast<size_t>(capacity_pairs)) * sizeof(long long));
+  CU(cudaMemcpy(host_out, ctx->trace_dev, n, cudaMemcpyDeviceToHost));
+  CU(cudaFree(ctx->trace_dev));
+  ctx->trace_dev = nullptr;
+  return 0;
+}
+
+int es_mma_bench(es_ctx* ctx, const int32_t* cfg15, int32_t grid, int64_t* cycles_host) {
+  if (!ctx || !cfg15 || !cycles_host || grid < 1 || grid > 1024) return ES_E_BADARG;
+  MmaBenchCfg c;
+  std::memcpy(&c, cfg15, sizeof(c));
+  long long* dev = nullptr;
+  CU(cudaMalloc(&dev, grid * sizeof(long long)));
+  CU(launch_mma_bench(c, grid, dev, nullptr));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(cycles_host, dev, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  CU(cudaFree(dev));
   return 0;
 }
 

@@ -31,6 +31,9 @@ struct ChainIO {
   long long dir_stride;
   const float* feat;     // [P,256]
   float* out_rgb;        // [P,3]
+  // debug: when non-null, CTA 0 records (clock64, code) pairs: trace[0] = count, then pairs (tools/trace_chain.py)
+  long long* trace;
+  int debug_flags;  // perf experiments only (ES_DEBUG_FLAGS): 1 = no weight copies, 2 = no A stores, 4 = no MMAs
 };
 
 cudaError_t launch_mlp_chain(int chain, bool tangent, bool use_deform, const ChainProg& prog, const ChainIO& io,
@@ -41,6 +44,16 @@ int mlp_chain_smem_bytes();
 cudaError_t launch_umma_probe(const uint16_t* a_f16 /*[128][64]*/, const uint16_t* b_f16 /*[256][64]*/,
                               float* d /*[128][256]*/, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int* err,
                               cudaStream_t stream);
+
+// ---- tcgen05 issue-rate microbenchmark (es_mmabench.cu)
+struct MmaBenchCfg {
+  int n;        // UMMA N (M = 128, K = 16 per instruction)
+  int iters;    // outer iterations; each issues `ksteps` MMAs
+  int ksteps;
+  int a_layout, a_lbo, a_sbo, a_kadv, a_tiles, a_tile_bytes;  // descriptor layout code / strides / K advance in bytes
+  int b_layout, b_lbo, b_sbo, b_kadv, b_tiles, b_tile_bytes;
+};
+cudaError_t launch_mma_bench(const MmaBenchCfg& cfg, int grid, long long* cycles_out, cudaStream_t stream);
 
 // ---- weight packing (es_pack.cu)
 // Gathers columns of an fp32 [n_out, n_in] matrix into the kernel's K order (colmap[k] = source column or -1),

@@ -19,7 +19,12 @@
 
 namespace es {
 
-constexpr int N_EPI_WARPS = 8;
+// Every 64-column chunk is split into NPART column parts of PCOLS columns; one epilogue warp owns one
+// (TMEM lane quadrant, part) pair, i.e. 32 rows x PCOLS columns of every chunk.  16 warps (4 per SM sub-partition)
+// hide the TMEM-load / MUFU / shuffle latencies far better than 8 (measured: tensor pipe 31 % -> see profiles/).
+constexpr int NPART = 4;
+constexpr int PCOLS = CHUNK_K / NPART;  // 16
+constexpr int N_EPI_WARPS = 4 * NPART;
 constexpr int N_EPI_THREADS = N_EPI_WARPS * 32;
 constexpr int N_THREADS = 64 + N_EPI_THREADS;
 
@@ -27,7 +32,7 @@ constexpr int N_THREADS = 64 + N_EPI_THREADS;
 constexpr int SM_A_OFF = 0;
 constexpr int SM_W_OFF = SM_A_OFF + NSLOT * SLOT_BYTES;    // 131072
 constexpr int SM_XCH_OFF = SM_W_OFF + NSTAGE * UNIT_BYTES;  // 196608
-constexpr int SM_XCH_BYTES = 2 * 2 * TILE_ROWS * 4 * 4;     // [parity][half][row][4] floats = 8192
+constexpr int SM_XCH_BYTES = 2 * NPART * TILE_ROWS * 4 * 4;  // [parity][part][row][4] floats
 constexpr int SM_BAR_OFF = SM_XCH_OFF + SM_XCH_BYTES;
 constexpr int N_BARS = 2 * NSLOT + 2 * NSTAGE + 4;
 constexpr int SM_TMEM_OFF = SM_BAR_OFF + N_BARS * 8;
@@ -81,30 +86,44 @@ __device__ __forceinline__ void static_for(F&& f) {
   }
 }
 
-// Fill v[32] with columns [32*HALF, 32*HALF+32) of encoder chunk SRC (K order: es_program.h chunk_feat).
+// does part PART of chunk SRC contain feature (var, freq, is_cos)?
+__host__ __device__ constexpr bool part_has(int src, int part, int var, int freq, int is_cos) {
+  for (int i = 0; i < PCOLS; ++i) {
+    const Feat f = chunk_feat(src, PCOLS * part + i);
+    if (f.var == var && f.freq == freq && f.is_cos == is_cos) return true;
+  }
+  return false;
+}
+
+// Fill v[PCOLS] with columns [PCOLS*PART, PCOLS*PART+PCOLS) of encoder chunk SRC (K order: es_program.h chunk_feat).
 // `pos` is the position the encoding is taken of (x for the deform net, x_c otherwise).  Tangent rows (s>0) get
 // the derivative of every feature wrt position component s-1.  All feature indices resolve at compile time, so
-// only the sin/cos pairs this half needs are evaluated and everything lives in registers.
-template <int SRC, int HALF, bool TANGENT>
-__device__ __forceinline__ void encode_half(float (&v)[32], const float (&pos)[3], const RowState& rs) {
+// only the sin/cos pairs this part needs are evaluated and everything lives in registers.
+template <int SRC, int PART, bool TANGENT>
+__device__ __forceinline__ void encode_part(float (&v)[PCOLS], const float (&pos)[3], const RowState& rs) {
   float var[10];
   var[0] = pos[0]; var[1] = pos[1]; var[2] = pos[2];
   var[3] = rs.t;
   var[4] = rs.g[0]; var[5] = rs.g[1]; var[6] = rs.g[2];
   var[7] = rs.dc[0]; var[8] = rs.dc[1]; var[9] = rs.dc[2];
   float sn[10][10], cs[10][10];
-  static_for<0, 32>([&](auto ic) {
+  static_for<0, PCOLS>([&](auto ic) {
     constexpr int i = decltype(ic)::value;
-    constexpr Feat f = chunk_feat(SRC, 32 * HALF + i);
-    if constexpr (f.var >= 0 && f.freq >= 0 && f.is_cos == 0) {
-      // reference: torch.sin(x * 2^k), torch.cos(x * 2^k)  (encoder.py:47-50); x*2^k is exact in fp32
-      sincosf(var[f.var] * static_cast<float>(1 << f.freq), &sn[f.var][f.freq], &cs[f.var][f.freq]);
+    constexpr Feat f = chunk_feat(SRC, PCOLS * PART + i);
+    if constexpr (f.var >= 0 && f.freq >= 0) {
+      // a sin column and its cos partner may land in different parts: evaluate the pair where either is needed,
+      // but only once per part (the sin column triggers it if present, else the cos column)
+      constexpr bool first = (f.is_cos == 0) || !part_has(SRC, PART, f.var, f.freq, 0);
+      if constexpr (first) {
+        // reference: torch.sin(x * 2^k), torch.cos(x * 2^k)  (encoder.py:47-50); x*2^k is exact in fp32
+        sincosf(var[f.var] * static_cast<float>(1 << f.freq), &sn[f.var][f.freq], &cs[f.var][f.freq]);
+      }
     }
   });
   const int s = rs.s;
-  static_for<0, 32>([&](auto ic) {
+  static_for<0, PCOLS>([&](auto ic) {
     constexpr int i = decltype(ic)::value;
-    constexpr Feat f = chunk_feat(SRC, 32 * HALF + i);
+    constexpr Feat f = chunk_feat(SRC, PCOLS * PART + i);
     if constexpr (f.var < 0) {
       v[i] = 0.f;
     } else {
@@ -128,78 +147,97 @@ __device__ __forceinline__ void encode_half(float (&v)[32], const float (&pos)[3
   });
 }
 
-// split v[32] into fp16 hi/lo and store as sub-block `half` of A ring slot `slot_base` for row `row`
-__device__ __forceinline__ void store_a_half(uint8_t* slot_base, int row, int half, const float (&v)[32]) {
+// split v[PCOLS] into fp16 hi/lo and store as column part `part` of A ring slot `slot_base` for row `row`
+__device__ __forceinline__ void store_a_part(uint8_t* slot_base, int row, int part, const float (&v)[PCOLS]) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < PCOLS / 8; ++g) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], hi[j], lo[j]);
-    uint8_t* p = slot_base + (4 * half + g) * A_LBO + row * 16;
+    uint8_t* p = slot_base + ((PCOLS / 8) * part + g) * A_LBO + row * 16;
     *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(p + SLOT_HALF_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// debug pipeline trace (CTA 0 only, off unless ChainIO::trace is set)
+__device__ __forceinline__ void trace_ev(long long* trace, int code) {
+  if (trace != nullptr && blockIdx.x == 0) {
+    unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(trace), 1ull);
+    if (i < 8000) {
+      trace[1 + 2 * i] = clock64();
+      trace[2 + 2 * i] = code;
+    }
+  }
+}
+
 struct EpiCtx {
   uint8_t* smem;
   Bars bars;
   uint32_t tmem_base;
   int* err;
   int row;     // 0..127 (TMEM lane)
-  int half;    // which 32 columns of every 64-wide chunk this thread owns
+  int part;    // which PCOLS columns of every 64-wide chunk this thread owns
   int lane;
   uint32_t ac;  // A-chunk counter (ring position), identical in all epilogue threads and the MMA warp
   uint32_t g;   // global MMA-layer counter (accumulator buffer = g & 1)
-  uint32_t xk;  // cross-half exchange counter
+  uint32_t xk;  // cross-part exchange counter
+  long long* trace;
+  bool tr;  // this thread records trace events
 };
 
-// sum a per-row float4 across the two column-half threads of the row (both get the total)
-__device__ __forceinline__ float4 cross_half_sum(EpiCtx& c, float4 part) {
+// sum a per-row float4 across the NPART column-part threads of the row (every one of them gets the total)
+__device__ __forceinline__ float4 cross_part_sum(EpiCtx& c, float4 part) {
   float4* xch = reinterpret_cast<float4*>(c.smem + SM_XCH_OFF);
   const int par = c.xk & 1;
   ++c.xk;
-  xch[(par * 2 + c.half) * TILE_ROWS + c.row] = part;
+  xch[(par * NPART + c.part) * TILE_ROWS + c.row] = part;
   named_bar_sync(1, N_EPI_THREADS);
-  float4 a = xch[(par * 2 + 0) * TILE_ROWS + c.row];
-  float4 b = xch[(par * 2 + 1) * TILE_ROWS + c.row];
-  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  float4 t = xch[(par * NPART + 0) * TILE_ROWS + c.row];
+#pragma unroll
+  for (int q = 1; q < NPART; ++q) {
+    float4 b = xch[(par * NPART + q) * TILE_ROWS + c.row];
+    t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+  }
+  return t;
 }
 
-// Read this thread's 32 columns of 64-col block `blk` of accumulator buffer `buf`, add bias, activate.
+// Read this thread's PCOLS columns of 64-col block `blk` of accumulator buffer `buf`, add bias, activate.
 // TANGENT rows (s>0): no bias, multiplied by the primal row's activation derivative (quad shuffle).
 template <int ACT, bool TANGENT>
 __device__ __forceinline__ void load_act(EpiCtx& c, int buf, int blk, const float* __restrict__ bias, int s,
-                                         float (&v)[32]) {
-  const int col0 = 64 * blk + 32 * c.half;
+                                         float (&v)[PCOLS]) {
+  const int col0 = 64 * blk + PCOLS * c.part;
   const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.row & ~31) << 16) + buf * HID + col0;
-  tmem_ld32(taddr, v);
-  tmem_ld_wait();
+  tmem_ld<PCOLS>(taddr, v);
+  // the bias loads overlap the TMEM read
+  float bj[PCOLS];
   const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < PCOLS / 4; ++q) {
     float4 bb = __ldg(b4 + q);
-    float bj[4] = {bb.x, bb.y, bb.z, bb.w};
+    bj[4 * q] = bb.x; bj[4 * q + 1] = bb.y; bj[4 * q + 2] = bb.z; bj[4 * q + 3] = bb.w;
+  }
+  const float bsel = (!TANGENT || s == 0) ? 1.f : 0.f;
+  tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = 4 * q + j;
-      float z = v[i] + ((!TANGENT || s == 0) ? bj[j] : 0.f);
-      float h, dh;
-      activate<ACT>(z, h, dh);
-      if (TANGENT) {
-        float dhp = __shfl_sync(0xffffffffu, dh, c.lane & ~3);
-        v[i] = (s == 0) ? h : dhp * v[i];
-      } else {
-        v[i] = h;
-      }
+  for (int i = 0; i < PCOLS; ++i) {
+    float z = fmaf(bj[i], bsel, v[i]);
+    float h, dh;
+    activate<ACT>(z, h, dh);
+    if (TANGENT) {
+      float dhp = __shfl_sync(0xffffffffu, dh, c.lane & ~3);
+      v[i] = (s == 0) ? h : dhp * v[i];
+    } else {
+      v[i] = h;
     }
   }
 }
 
 template <bool TANGENT>
 __device__ __forceinline__ void load_act_dyn(EpiCtx& c, int act, int buf, int blk, const float* bias, int s,
-                                             float (&v)[32]) {
+                                             float (&v)[PCOLS]) {
   if (act == ACT_RELU) load_act<ACT_RELU, TANGENT>(c, buf, blk, bias, s, v);
   else if (act == ACT_SOFTPLUS100) load_act<ACT_SOFTPLUS100, TANGENT>(c, buf, blk, bias, s, v);
   else load_act<ACT_NONE, TANGENT>(c, buf, blk, bias, s, v);
@@ -207,27 +245,28 @@ __device__ __forceinline__ void load_act_dyn(EpiCtx& c, int act, int buf, int bl
 
 // acc[j] += sum_i v[i] * w[j][col0 + i]   (w row stride 256, uniform loads)
 template <int NOUT>
-__device__ __forceinline__ void dot_accum(const float (&v)[32], const float* __restrict__ w, int col0,
+__device__ __forceinline__ void dot_accum(const float (&v)[PCOLS], const float* __restrict__ w, int col0,
                                           float (&acc)[4]) {
 #pragma unroll
   for (int j = 0; j < NOUT; ++j) {
     const float4* w4 = reinterpret_cast<const float4*>(w + j * HID + col0);
-    float a = acc[j];
+    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < PCOLS / 4; ++q) {
       float4 ww = __ldg(w4 + q);
-      a = fmaf(v[4 * q + 0], ww.x, a);
-      a = fmaf(v[4 * q + 1], ww.y, a);
-      a = fmaf(v[4 * q + 2], ww.z, a);
-      a = fmaf(v[4 * q + 3], ww.w, a);
+      a0 = fmaf(v[4 * q + 0], ww.x, a0);
+      a1 = fmaf(v[4 * q + 1], ww.y, a1);
+      a0 = fmaf(v[4 * q + 2], ww.z, a0);
+      a1 = fmaf(v[4 * q + 3], ww.w, a1);
     }
-    acc[j] = a;
+    acc[j] += a0 + a1;
   }
 }
 
 __device__ __forceinline__ void wait_d_full(EpiCtx& c, uint32_t g_layer) {
   mbar_wait(&c.bars.d_full[g_layer & 1], (g_layer >> 1) & 1, c.err, 100 + static_cast<int>(g_layer & 1));
   tc_fence_after();
+  if (c.tr) trace_ev(c.trace, 4000 + static_cast<int>(g_layer % 100));  // EPI: accumulator of layer g ready
 }
 __device__ __forceinline__ void release_d(EpiCtx& c, uint32_t g_layer) {
   tc_fence_before();
@@ -243,19 +282,22 @@ __device__ __forceinline__ float4 tail_dot(EpiCtx& c, uint32_t g_layer, int act,
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
   for (int blk = 0; blk < 4; ++blk) {
-    float v[32];
+    float v[PCOLS];
     load_act_dyn<TANGENT>(c, act, g_layer & 1, blk, bias, s, v);
-    dot_accum<NOUT>(v, w_out, 64 * blk + 32 * c.half, acc);
+    dot_accum<NOUT>(v, w_out, 64 * blk + PCOLS * c.part, acc);
   }
   release_d(c, g_layer);
-  return cross_half_sum(c, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  return cross_part_sum(c, make_float4(acc[0], acc[1], acc[2], acc[3]));
 }
 
 template <int SRC, bool TANGENT>
-__device__ __forceinline__ void encode_dispatch(EpiCtx& c, float (&v)[32], const float (&pos)[3],
+__device__ __forceinline__ void encode_dispatch(EpiCtx& c, float (&v)[PCOLS], const float (&pos)[3],
                                                 const RowState& rs) {
-  if (c.half == 0) encode_half<SRC, 0, TANGENT>(v, pos, rs);
-  else encode_half<SRC, 1, TANGENT>(v, pos, rs);
+  // c.part is warp-uniform: no divergence
+  static_for<0, NPART>([&](auto pc) {
+    constexpr int P = decltype(pc)::value;
+    if (c.part == P) encode_part<SRC, P, TANGENT>(v, pos, rs);
+  });
 }
 
 template <int CHAIN, bool TANGENT, bool USE_DEFORM>
@@ -311,63 +353,75 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         for (int u = 0; u < prog.units_per_tile; u += step) {
           const uint32_t st = wc % NSTAGE;
           mbar_wait(&bars.w_empty[st], ((wc / NSTAGE) & 1) ^ 1, err, 200);
-          mbar_arrive_expect_tx(&bars.w_full[st], UNIT_BYTES);
-          tma_bulk_g2s(smem + SM_W_OFF + st * UNIT_BYTES, prog.w_units + static_cast<size_t>(u) * UNIT_BYTES,
-                       UNIT_BYTES, &bars.w_full[st]);
+          if ((io.debug_flags & 1) && wc >= NSTAGE) {
+            mbar_arrive(&bars.w_full[st]);
+          } else {
+            mbar_arrive_expect_tx(&bars.w_full[st], UNIT_BYTES);
+            tma_bulk_g2s(smem + SM_W_OFF + st * UNIT_BYTES, prog.w_units + static_cast<size_t>(u) * UNIT_BYTES,
+                         UNIT_BYTES, &bars.w_full[st]);
+          }
           ++wc;
         }
       }
     }
   } else if (warp == 1) {
     // ============================================================== MMA issuer
+    // One thread feeds the tensor pipe; it must stay well ahead of the 128 cycles an M128 N256 K16 UMMA takes, so
+    // the loop body is a handful of 64-bit adds on precomputed descriptors (a naive loop that rebuilt the
+    // descriptors cost ~285 cycles per MMA and capped the tensor pipe at 31 %, profiles/r1_ncu_summary_v1.txt).
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(TILE_ROWS, HID);
       uint32_t wc = 0, ac = 0, g = 0;
-      const uint32_t a_base = smem_u32(smem + SM_A_OFF);
-      const uint32_t w_base = smem_u32(smem + SM_W_OFF);
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(smem + SM_A_OFF), A_LBO, A_SBO);
+      const uint64_t w_desc0 = make_smem_desc(smem_u32(smem + SM_W_OFF), B_LBO, B_SBO);
+      constexpr uint64_t A_KS = (2 * A_LBO) >> 4;          // one K=16 step inside a slot plane
+      constexpr uint64_t A_LO = SLOT_HALF_BYTES >> 4;      // hi plane -> lo plane
+      constexpr uint64_t A_SB = (4 * A_LBO) >> 4;          // one 32-wide sub-block
+      constexpr uint64_t W_KS = (2 * B_LBO) >> 4;
+      const bool three = prog.n_terms == 3;
+      const bool do_mma = !(io.debug_flags & 4);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < prog.n_layers; ++l, ++g) {
           const LayerProg& L = prog.layer[l];
+          const int n_chunks = L.n_chunks;
           const uint32_t d_tmem = tmem_base + (g & 1) * HID;
           mbar_wait(&bars.d_empty[g & 1], ((g >> 1) & 1) ^ 1, err, 300 + static_cast<int>(g & 1));
           tc_fence_after();
+          trace_ev(io.trace, 1000 + l);  // MMA: accumulator free, layer l starts
           uint32_t accum = 0;
-          for (int ck = 0; ck < L.n_chunks; ++ck, ++ac) {
+          for (int ck = 0; ck < n_chunks; ++ck, ++ac) {
             const uint32_t slot = ac % NSLOT;
+            const int nsub = L.nsub[ck];
             mbar_wait(&bars.a_full[slot], (ac / NSLOT) & 1, err, 310);
             tc_fence_after();
-            const uint32_t a_slot = a_base + slot * SLOT_BYTES;
-            for (int sb = 0; sb < L.nsub[ck]; ++sb) {
+            trace_ev(io.trace, 2000 + l * 16 + ck);  // MMA: chunk ck of layer l available
+            uint64_t a_hi = a_desc0 + static_cast<uint64_t>(slot * (SLOT_BYTES >> 4));
+            for (int sb = 0; sb < nsub; ++sb, a_hi += A_SB) {
               // ---- hi weight unit: A_hi*B_hi and A_lo*B_hi
               {
                 const uint32_t st = wc % NSTAGE;
                 mbar_wait(&bars.w_full[st], (wc / NSTAGE) & 1, err, 320);
                 tc_fence_after();
-                const uint32_t w_st = w_base + st * UNIT_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t bd = make_smem_desc(w_st + ks * 2 * B_LBO, B_LBO, B_SBO);
-                  const uint32_t a_off = (sb * 4 + ks * 2) * A_LBO;
-                  umma_f16_ss(d_tmem, make_smem_desc(a_slot + a_off, A_LBO, A_SBO), bd, idesc, accum);
-                  accum = 1;
-                  if (prog.n_terms == 3)
-                    umma_f16_ss(d_tmem, make_smem_desc(a_slot + SLOT_HALF_BYTES + a_off, A_LBO, A_SBO), bd, idesc,
-                                 1);
+                const uint64_t wd = w_desc0 + static_cast<uint64_t>(st * (UNIT_BYTES >> 4));
+                if (do_mma) {
+                  umma_f16_ss(d_tmem, a_hi, wd, idesc, accum);
+                  if (three) umma_f16_ss(d_tmem, a_hi + A_LO, wd, idesc, 1);
+                  umma_f16_ss(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
+                  if (three) umma_f16_ss(d_tmem, a_hi + A_LO + A_KS, wd + W_KS, idesc, 1);
                 }
+                accum = 1;
                 umma_commit(&bars.w_empty[st]);
                 ++wc;
               }
               // ---- lo weight unit: A_hi*B_lo
-              if (prog.n_terms == 3) {
+              if (three) {
                 const uint32_t st = wc % NSTAGE;
                 mbar_wait(&bars.w_full[st], (wc / NSTAGE) & 1, err, 321);
                 tc_fence_after();
-                const uint32_t w_st = w_base + st * UNIT_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t bd = make_smem_desc(w_st + ks * 2 * B_LBO, B_LBO, B_SBO);
-                  const uint32_t a_off = (sb * 4 + ks * 2) * A_LBO;
-                  umma_f16_ss(d_tmem, make_smem_desc(a_slot + a_off, A_LBO, A_SBO), bd, idesc, 1);
+                const uint64_t wd = w_desc0 + static_cast<uint64_t>(st * (UNIT_BYTES >> 4));
+                if (do_mma) {
+                  umma_f16_ss(d_tmem, a_hi, wd, idesc, 1);
+                  umma_f16_ss(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
                 }
                 umma_commit(&bars.w_empty[st]);
                 ++wc;
@@ -376,6 +430,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
             umma_commit(&bars.a_empty[slot]);
           }
           umma_commit(&bars.d_full[g & 1]);
+          trace_ev(io.trace, 3000 + l);  // MMA: all MMAs of layer l issued
         }
       }
     }
@@ -387,11 +442,13 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
     c.tmem_base = tmem_base;
     c.err = err;
     c.lane = lane;
-    c.half = (warp - 2) >> 2;
+    c.part = (warp - 2) >> 2;
     c.row = (warp & 3) * 32 + lane;
     c.ac = 0;
     c.g = 0;
     c.xk = 0;
+    c.trace = io.trace;
+    c.tr = (warp == 2 && lane == 0);
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       // ---------------------------------------------------------- row state
@@ -455,14 +512,14 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
               prim[i] = rs.x[i] + dl[i] + __ldg(prog.deform_out_b + i);
               rs.xc[i] = __shfl_sync(0xffffffffu, prim[i], lane & ~3);
             }
-            if (c.half == 0 && rs.valid && rs.s > 0 && io.out_jac) {
+            if (c.part == 0 && rs.valid && rs.s > 0 && io.out_jac) {
               // column j = s-1 of J = I + dDelta/dx ; J stored [i][j] row-major
 #pragma unroll
               for (int i = 0; i < 3; ++i)
                 io.out_jac[rs.pt * 9 + 3 * i + (rs.s - 1)] = dl[i] + ((i == rs.s - 1) ? 1.f : 0.f);
             }
           }
-          if (c.half == 0 && rs.valid && rs.s == 0 && io.out_xc) {
+          if (c.part == 0 && rs.valid && rs.s == 0 && io.out_xc) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) io.out_xc[rs.pt * 3 + i] = rs.xc[i];
           }
@@ -476,7 +533,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           const uint32_t slot = c.ac % NSLOT;
           mbar_wait(&bars.a_empty[slot], ((c.ac / NSLOT) & 1) ^ 1, err, 400);
           uint8_t* slot_base = smem + SM_A_OFF + slot * SLOT_BYTES;
-          float v[32];
+          float v[PCOLS];
           const int src = L.src[ck];
           bool active = true;
           if (src == SRC_PREV) {
@@ -485,7 +542,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
               prev_waited = true;
             }
             load_act_dyn<TANGENT>(c, act_prev, (c.g - 1) & 1, L.arg[ck], bias_prev, rs.s, v);
-            if (L.side_dot) dot_accum<1>(v, prog.sdf_out_w, 64 * L.arg[ck] + 32 * c.half, sdf_acc);
+            if (L.side_dot) dot_accum<1>(v, prog.sdf_out_w, 64 * L.arg[ck] + PCOLS * c.part, sdf_acc);
             if (--n_prev_left == 0) release_d(c, c.g - 1);
           } else if (src == SRC_ENC_DEFORM) {
             encode_dispatch<SRC_ENC_DEFORM, TANGENT>(c, v, rs.x, rs);
@@ -494,25 +551,27 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           } else if (src == SRC_COLOR_A) {
             encode_dispatch<SRC_COLOR_A, false>(c, v, rs.xc, rs);
           } else if (src == SRC_COLOR_B) {
-            if (c.half == 0) encode_half<SRC_COLOR_B, 0, false>(v, rs.xc, rs);
+            if (PCOLS * c.part < 32) encode_dispatch<SRC_COLOR_B, false>(c, v, rs.xc, rs);  // 32-wide chunk
             else active = false;
           } else {  // SRC_FEAT
-            const float4* f4 = reinterpret_cast<const float4*>(io.feat + rs.pt * HID + 64 * L.arg[ck] + 32 * c.half);
+            const float4* f4 =
+                reinterpret_cast<const float4*>(io.feat + rs.pt * HID + 64 * L.arg[ck] + PCOLS * c.part);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < PCOLS / 4; ++q) {
               float4 f = __ldg(f4 + q);
               v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
             }
           }
-          if (active) store_a_half(slot_base, c.row, c.half, v);
+          if (active && !(io.debug_flags & 2)) store_a_part(slot_base, c.row, c.part, v);
           fence_proxy_async_smem();
           mbar_arrive(&bars.a_full[slot]);
+          if (c.tr) trace_ev(io.trace, 5000 + l * 16 + ck);  // EPI: chunk ck of layer l written
         }
 
         if (L.side_dot) {
           // sdf row of the SDF output layer: primal rows -> sdf, tangent rows -> g_c[s-1]
-          float4 r = cross_half_sum(c, make_float4(sdf_acc[0], 0.f, 0.f, 0.f));
-          if (c.half == 0 && rs.valid) {
+          float4 r = cross_part_sum(c, make_float4(sdf_acc[0], 0.f, 0.f, 0.f));
+          if (c.part == 0 && rs.valid) {
             if (rs.s == 0) {
               if (io.out_sdf) io.out_sdf[rs.pt] = r.x + __ldg(prog.sdf_out_b);
             } else if (io.out_gc) {
@@ -528,7 +587,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       const int act_last = prog.layer[last].act;
       if (prog.post_op == POST_SDF_TAIL) {
         float4 r = tail_dot<1, TANGENT>(c, c.g - 1, act_last, bias_last, prog.sdf_out_w, rs.s);
-        if (c.half == 0 && rs.valid) {
+        if (c.part == 0 && rs.valid) {
           if (rs.s == 0) {
             if (io.out_sdf) io.out_sdf[rs.pt] = r.x + __ldg(prog.sdf_out_b);
           } else if (io.out_gc) {
@@ -537,7 +596,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         }
       } else if (prog.post_op == POST_COLOR_TAIL) {
         float4 r = tail_dot<3, false>(c, c.g - 1, act_last, bias_last, prog.color_out_w, 0);
-        if (c.half == 0 && rs.valid) {
+        if (c.part == 0 && rs.valid) {
           float o[3] = {r.x, r.y, r.z};
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -549,13 +608,14 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         wait_d_full(c, c.g - 1);
 #pragma unroll 1
         for (int blk = 0; blk < 4; ++blk) {
-          float v[32];
+          float v[PCOLS];
           // feat = D + bias (no activation); tangent rows are not needed
           load_act<ACT_NONE, false>(c, (c.g - 1) & 1, blk, prog.feat_out_b, 0, v);
           if (rs.valid && rs.s == 0) {
-            float4* o4 = reinterpret_cast<float4*>(io.out_feat + rs.pt * HID + 64 * blk + 32 * c.half);
+            float4* o4 = reinterpret_cast<float4*>(io.out_feat + rs.pt * HID + 64 * blk + PCOLS * c.part);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int q = 0; q < PCOLS / 4; ++q)
+              o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
         release_d(c, c.g - 1);

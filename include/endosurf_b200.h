@@ -124,6 +124,13 @@ int64_t es_launch_count(const es_ctx* ctx);
  * 64 chunk columns reads for network `net` (or -1 for padding).  src: 1 deform enc, 2 sdf enc, 3 colour A, 4 colour B. */
 int es_chunk_colmap(const es_ctx* ctx, int net, int src, int32_t* out64);
 
+/* Debug: pipeline trace of CTA 0 of the next fused-chain launches.  host_out == NULL arms it; a second call with a
+ * buffer of 1 + 2*capacity_pairs int64 copies out [count, (clock64, code) ...] and disarms (tools/trace_chain.py). */
+int es_debug_trace(es_ctx* ctx, int64_t* host_out, int64_t capacity_pairs);
+
+/* Debug: tcgen05 issue-rate microbenchmark (tools/mma_bench.py); cfg15 = the 15 int32 fields of es::MmaBenchCfg. */
+int es_mma_bench(es_ctx* ctx, const int32_t* cfg15, int32_t grid, int64_t* cycles_host);
+
 /* tcgen05 self-test: d[128,256] = a[128,64] (fp16 bits) * b[256,64]^T (fp16 bits) through the same shared-memory
  * descriptors / TMA / TMEM path as the fused kernels.  lbo/sbo <= 0 selects the built-in strides. */
 int es_umma_probe(es_ctx* ctx, const uint16_t* a, const uint16_t* b, float* d, int32_t a_lbo, int32_t a_sbo,

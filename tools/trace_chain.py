@@ -1,0 +1,26 @@
+"""Pipeline trace of one CTA of a fused chain (GPU box): python tools/trace_chain.py [sdfq|geom|color]"""
+import copy, ctypes as C, os, sys, numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import load_cfg, load_ckpt
+from endosurf_b200 import EndoSurfRenderer, _lib
+which = sys.argv[1] if len(sys.argv) > 1 else "geom"
+cfg = load_cfg(); r = EndoSurfRenderer(cfg["render"], cfg["net"], device="cuda"); r.load_checkpoint(load_ckpt()); r.eval()
+n = 148 * 128 * 4
+x = torch.rand(n, 3, device="cuda") - 0.5; t = torch.rand(n, device="cuda"); d = torch.randn(n, 3, device="cuda")
+lib, ctx = _lib.load(), r._context()
+fn = (lambda: r.sdf_from_observed_space(x, t)) if which == "sdfq" else (lambda: r.point_forward(x, d, t))
+fn(); torch.cuda.synchronize()
+lib.es_debug_trace(ctx, None, 0)
+fn(); torch.cuda.synchronize()
+buf = np.zeros(1 + 2 * 8000, dtype=np.int64)
+lib.es_debug_trace(ctx, buf.ctypes.data_as(C.c_void_p), 8000)
+cnt = int(min(buf[0], 8000)); ev = buf[1:1 + 2 * cnt].reshape(-1, 2)
+ev = ev[np.argsort(ev[:, 0])]; t0 = ev[0, 0]
+names = {1: "MMA layer start", 2: "MMA chunk ready", 3: "MMA layer issued", 4: "EPI acc ready", 5: "EPI chunk written"}
+print("events", cnt)
+last = {}
+for clk, code in ev[:400]:
+    k = code // 1000; rest = code % 1000
+    what = f"L{rest}" if k in (1, 3, 4) else f"L{rest // 16} c{rest % 16}"
+    print(f"{clk - t0:9d}  {names[k]:18s} {what}")
