@@ -49,6 +49,10 @@ EXPORTS = {
     "es_point_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    "es_train_layout": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "es_point_forward_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                         C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 11),
+    "es_point_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 7),
     "es_up_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "es_render_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(EsRenderParams),

@@ -59,6 +59,10 @@ struct es_ctx {
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
   ChainProg prog_sdfq{}, prog_geom{}, prog_color{};
+  // reverse (training) chains: transposed weight units + programs, index = ES_NET_*
+  uint8_t* rev_units[3] = {nullptr, nullptr, nullptr};
+  int rev_layers[3] = {0, 0, 0};
+  ChainProg prog_rev[3]{};
   // optional per-kernel timing (es_profile_*)
   bool profiling = false;
   long long* trace_dev = nullptr;  // debug pipeline trace buffer (es_debug_trace)
@@ -286,6 +290,51 @@ void build_chain_programs(es_ctx* ctx) {
   c.units_per_tile = static_cast<int>(ctx->color_units_n);
   c.post_op = POST_COLOR_TAIL;
   ctx->prog_color = c;
+
+  // ---- reverse chains (es_point_backward): standard 4-chunk 256x256 layers on transposed weights
+  const int L = cfg.n_layers;
+  const int LdS = cfg.use_deform ? L - 1 : 0;  // geometry-chain slot offset of the sdf layers
+  auto rev_layer = [&](LayerProg& G, uint8_t src, int stash_slot, int zbar_slot, uint8_t act, bool rank1) {
+    std::memset(&G, 0, sizeof(G));
+    G.n_chunks = 4;
+    for (int k = 0; k < 4; ++k) {
+      G.src[k] = src;
+      G.arg[k] = static_cast<uint8_t>(k);
+      G.nsub[k] = 2;
+    }
+    G.stash_slot = static_cast<uint8_t>(stash_slot);
+    G.zbar_slot = static_cast<uint8_t>(zbar_slot);
+    G.bwd_act = act;
+    G.rank1 = rank1 ? 1 : 0;
+  };
+  for (int net = 0; net < 3; ++net) {
+    ChainProg r{};
+    common(r);
+    r.bias = ctx->geom_bias;
+    r.w_units = ctx->rev_units[net];
+    r.post_op = POST_BWD_DUMP;
+    r.post_zbar_slot = 0;
+    int n = 0;
+    if (net == ES_NET_SDF) {
+      rev_layer(r.layer[n++], SRC_ADJ_FEAT, 0, 0, ACT_SOFTPLUS100, false);   // S_{L-1}^T (feature rows)
+      for (int m = L - 2; m >= 1; --m)                                        // S_m^T
+        rev_layer(r.layer[n++], SRC_BWD_PREV, LdS + m + 1, m, ACT_SOFTPLUS100, m == L - 2);
+      r.post_stash_slot = LdS + 1;
+      r.post_bwd_act = ACT_SOFTPLUS100;
+    } else {
+      const int tail_slot = net == ES_NET_DEFORM ? L - 1 : static_cast<int>(C.progs.size());
+      for (int m = L - 2; m >= 1; --m)
+        rev_layer(r.layer[n++], m == L - 2 ? SRC_BWD_OUTER3 : SRC_BWD_PREV, m == L - 2 ? tail_slot : m + 1, m,
+                  ACT_RELU, false);
+      r.post_stash_slot = 1;
+      r.post_bwd_act = ACT_RELU;
+      r.outer3_w = net == ES_NET_DEFORM ? ctx->small + SM_DEFORM_W : ctx->small + SM_COLOR_W;
+    }
+    r.n_layers = n;
+    r.units_per_tile = n * 16;
+    ctx->rev_layers[net] = n;
+    ctx->prog_rev[net] = r;
+  }
 }
 
 }  // namespace
@@ -358,6 +407,10 @@ int es_create(es_ctx** out, const es_net_config* cfg) {
   CUC(cudaMalloc(&ctx->geom_bias, static_cast<size_t>(Ld + Ls) * HID * sizeof(float)));
   CUC(cudaMalloc(&ctx->color_bias, C.packs.size() * HID * sizeof(float)));
   CUC(cudaMalloc(&ctx->small, SM_TOTAL_F * sizeof(float)));
+  for (int net = 0; net < 3; ++net) {
+    const int nl = net == ES_NET_SDF ? c.n_layers - 1 : c.n_layers - 2;
+    CUC(cudaMalloc(&ctx->rev_units[net], static_cast<size_t>(nl) * 16 * UNIT_BYTES));
+  }
   CUC(cudaMalloc(&ctx->err_dev, sizeof(int)));
   CUC(cudaMemset(ctx->geom_bias, 0, static_cast<size_t>(Ld + Ls) * HID * sizeof(float)));
   CUC(cudaMemset(ctx->color_bias, 0, C.packs.size() * HID * sizeof(float)));
@@ -384,6 +437,7 @@ void es_destroy(es_ctx* ctx) {
   cudaFree(ctx->color_bias);
   cudaFree(ctx->small);
   cudaFree(ctx->err_dev);
+  for (int net = 0; net < 3; ++net) cudaFree(ctx->rev_units[net]);
   cudaFree(ctx->ws);
   for (int net = 0; net < 3; ++net)
     for (auto& k : ctx->plan[net].packs) cudaFree(k.colmap_dev);
@@ -445,6 +499,23 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
     CU(cudaMemcpyAsync(ctx->small + SM_COLOR_W, wl, 3 * HID * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     CU(cudaMemcpyAsync(ctx->small + SM_COLOR_B, bl, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }
+  // transposed units for the reverse (training) chains
+  {
+    const float inv_sqrt2 = static_cast<float>(1.0 / std::sqrt(2.0));
+    const int skip = ctx->cfg.skip_layer;
+    uint8_t* ru = ctx->rev_units[net];
+    int r = 0;
+    if (net == ES_NET_SDF) {
+      CU(launch_pack_layer_T(w[L - 1] + P.in_dims[L - 1], HID, P.in_dims[L - 1], HID, 1.f,
+                             ru + static_cast<size_t>(r++) * 16 * UNIT_BYTES, stream));
+      ++ctx->launches;
+    }
+    for (int m = L - 2; m >= 1; --m) {
+      CU(launch_pack_layer_T(w[m], P.out_dims[m], P.in_dims[m], P.out_dims[m - 1], m == skip ? inv_sqrt2 : 1.f,
+                             ru + static_cast<size_t>(r++) * 16 * UNIT_BYTES, stream));
+      ++ctx->launches;
+    }
+  }
   ctx->loaded[net] = true;
   return 0;
 }
@@ -495,9 +566,10 @@ int es_sdf_query(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int
   return timed_chain(ctx, 2, CHAIN_SDF, false, ctx->prog_sdfq, io, static_cast<cudaStream_t>(stream));
 }
 
-int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride, const float* dirs,
-                     int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac, float* sdf, float* g_c,
-                     float* feat, float* rgb, void* stream_) {
+static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
+                              const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
+                              float* sdf, float* g_c, float* feat, float* rgb, uint16_t* gs_hi, uint16_t* gs_lo,
+                              uint16_t* cs_hi, uint16_t* cs_lo, void* stream_) {
   if (!ctx || n < 0 || t_div <= 0) return ES_E_BADARG;
   if (n == 0) return 0;
   if (!x) return ES_E_BADARG;
@@ -535,6 +607,9 @@ int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div,
   io.out_sdf = sdf;
   io.out_gc = g_c;
   io.out_feat = feat;
+  io.stash_hi = gs_hi;
+  io.stash_lo = gs_lo;
+  io.stash_rows = ((n + 31) / 32) * TILE_ROWS;
   if (int r = timed_chain(ctx, 0, CHAIN_SDF, true, ctx->prog_geom, io, stream)) return r;
   if (!ctx->cfg.use_deform)  // canonical = observed space (endosurf.py:576-577)
     CU(cudaMemcpyAsync(x_c, x, static_cast<size_t>(n) * 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -558,8 +633,66 @@ int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div,
     ic.dir_stride = dir_stride;
     ic.feat = feat;
     ic.out_rgb = rgb;
+    ic.stash_hi = cs_hi;
+    ic.stash_lo = cs_lo;
+    ic.stash_rows = ((n + TILE_ROWS - 1) / TILE_ROWS) * TILE_ROWS;
     if (int r = timed_chain(ctx, 1, CHAIN_COLOR, false, ctx->prog_color, ic, stream)) return r;
   }
+  return 0;
+}
+
+int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride, const float* dirs,
+                     int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac, float* sdf, float* g_c,
+                     float* feat, float* rgb, void* stream) {
+  return point_forward_impl(ctx, x, t, t_div, t_stride, dirs, dir_div, dir_stride, n, x_c, jac, sdf, g_c, feat, rgb,
+                            nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int es_train_layout(const es_ctx* ctx, int64_t n, int64_t* out6) {
+  if (!ctx || !out6 || n < 0) return ES_E_BADARG;
+  out6[0] = ((n + 31) / 32) * TILE_ROWS;                       // geometry stash rows (4 rows per point)
+  out6[1] = ctx->prog_geom.n_layers;                           // geometry stash slots
+  out6[2] = ((n + TILE_ROWS - 1) / TILE_ROWS) * TILE_ROWS;     // colour stash rows
+  out6[3] = ctx->prog_color.n_layers + 1;                      // colour stash slots (+ output-layer input)
+  out6[4] = ctx->cfg.n_layers - 1;                             // zbar slots of each reverse chain (forward layer m)
+  out6[5] = ctx->cfg.use_deform ? ctx->cfg.n_layers - 1 : 0;   // geometry slot offset of the sdf layers
+  return 0;
+}
+
+int es_point_forward_train(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
+                           const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
+                           float* sdf, float* g_c, float* feat, float* rgb, uint16_t* geom_stash_hi,
+                           uint16_t* geom_stash_lo, uint16_t* color_stash_hi, uint16_t* color_stash_lo, void* stream) {
+  if (!x_c || !sdf || !g_c || !feat || !geom_stash_hi || !geom_stash_lo) return ES_E_BADARG;
+  if (rgb && (!color_stash_hi || !color_stash_lo)) return ES_E_BADARG;
+  return point_forward_impl(ctx, x, t, t_div, t_stride, dirs, dir_div, dir_stride, n, x_c, jac, sdf, g_c, feat, rgb,
+                            geom_stash_hi, geom_stash_lo, color_stash_hi, color_stash_lo, stream);
+}
+
+int es_point_backward(es_ctx* ctx, int net, int64_t n, const uint16_t* stash_hi, const uint16_t* stash_lo,
+                      const float* adj, const float* adj_feat, uint16_t* zbar_hi, uint16_t* zbar_lo, void* stream) {
+  if (!ctx || net < 0 || net > 2 || n < 0 || !stash_hi || !stash_lo || !adj || !zbar_hi || !zbar_lo)
+    return ES_E_BADARG;
+  if (net == ES_NET_SDF && !adj_feat) return fail(ctx, ES_E_BADARG, "adj_feat required for the sdf chain");
+  if (net == ES_NET_DEFORM && !ctx->cfg.use_deform) return fail(ctx, ES_E_BADARG, "no deformation network");
+  if (int r = check_loaded(ctx, true)) return r;
+  if (n == 0) return 0;
+  ChainIO io{};
+  io.n_points = n;
+  io.err = ctx->err_dev;
+  io.stash_hi = const_cast<uint16_t*>(stash_hi);
+  io.stash_lo = const_cast<uint16_t*>(stash_lo);
+  const bool tangent = net != ES_NET_COLOR;
+  io.stash_rows = tangent ? ((n + 31) / 32) * TILE_ROWS : ((n + TILE_ROWS - 1) / TILE_ROWS) * TILE_ROWS;
+  io.zbar_hi = zbar_hi;
+  io.zbar_lo = zbar_lo;
+  io.adj = adj;
+  io.adj_feat = adj_feat;
+  io.t_div = 1;
+  io.dir_div = 1;
+  CU(launch_mlp_chain(tangent ? CHAIN_SDF : CHAIN_COLOR, tangent, true, ctx->prog_rev[net], io, ctx->n_sms,
+                      static_cast<cudaStream_t>(stream), true));
+  ++ctx->launches;
   return 0;
 }
 
@@ -576,9 +709,13 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
                    const es_render_out* out, void* stream_) {
   if (!ctx || !p || !out || n_rays < 0) return ES_E_BADARG;
   if (n_rays == 0) return 0;
-  if (!rays || !p->variance || !out->color_map || !out->depth_map || !out->gradients_o || !out->gradient_o_error ||
-      !out->weights || !out->weight_max || !out->cdf || !out->s_val)
+  const bool sample_only = out->color_map == nullptr;  // hierarchical sampling only (training path): z_vals out
+  if (sample_only) {
+    if (!rays || !out->z_vals || p->z_override) return fail(ctx, ES_E_BADARG, "sampling-only call needs rays and z_vals");
+  } else if (!rays || !p->variance || !out->depth_map || !out->gradients_o || !out->gradient_o_error ||
+             !out->weights || !out->weight_max || !out->cdf || !out->s_val) {
     return fail(ctx, ES_E_BADARG, "null input/output pointer");
+  }
   if (int r = check_loaded(ctx, true)) return r;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int ns = p->n_samples;
@@ -670,6 +807,10 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
         }
       }
     }
+    if (sample_only) {
+      CU(cudaMemcpyAsync(out->z_vals + r0 * M, z, R * M * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+      continue;
+    }
     // render_core (endosurf.py:134-213)
     CU(launch_points_from_z(rg, z, n, 1, sample_dist, pts, stream));
     ++ctx->launches;
@@ -693,6 +834,7 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
     if (out->z_vals && z != out->z_vals + r0 * M)
       CU(cudaMemcpyAsync(out->z_vals + r0 * M, z, R * M * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }
+  if (sample_only) return 0;
   CU(launch_eikonal_reduce(eik, n_rays, out->gradient_o_error, stream));
   ++ctx->launches;
   return 0;

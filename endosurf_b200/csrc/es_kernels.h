@@ -31,13 +31,21 @@ struct ChainIO {
   long long dir_stride;
   const float* feat;     // [P,256]
   float* out_rgb;        // [P,3]
+  // training: activation stash (fp16 hi/lo planes, [slot][stash_rows][256], row = tile*128 + tile row)
+  uint16_t* stash_hi;      // forward-train: written; reverse: read
+  uint16_t* stash_lo;
+  long long stash_rows;
+  uint16_t* zbar_hi;       // reverse: adjoints of the forward pre-activations, same layout, [zbar slot]
+  uint16_t* zbar_lo;
+  const float* adj;        // reverse: [logical row][4] = (o.x, o.y, o.z, r)  (logical row = 4*pt+s or pt)
+  const float* adj_feat;   // reverse sdf chain: d loss / d feat [P,256]
   // debug: when non-null, CTA 0 records (clock64, code) pairs: trace[0] = count, then pairs (tools/trace_chain.py)
   long long* trace;
   int debug_flags;  // perf experiments only (ES_DEBUG_FLAGS): 1 = no weight copies, 2 = no A stores, 4 = no MMAs
 };
 
 cudaError_t launch_mlp_chain(int chain, bool tangent, bool use_deform, const ChainProg& prog, const ChainIO& io,
-                             int n_sms, cudaStream_t stream);
+                             int n_sms, cudaStream_t stream, bool bwd = false);
 int mlp_chain_smem_bytes();
 
 // ---- tcgen05 layout self-test (es_probe.cu): one 128x256x64 fp16 GEMM through the same descriptors
@@ -61,6 +69,10 @@ cudaError_t launch_mma_bench(const MmaBenchCfg& cfg, int grid, long long* cycles
 // [hi(sub0), lo(sub0), hi(sub1), lo(sub1), ...] in the canonical no-swizzle K-major UMMA layout.
 cudaError_t launch_pack_layer(const float* w, int n_out, int n_in, const int* colmap_dev, int k_total, float scale,
                               uint8_t* units_out, cudaStream_t stream);
+// Transposed pack for the reverse chains: B[n][k] = w[k][n] * scale for k < k_valid (forward out-features),
+// n < n_valid (forward in-features kept: the first 256 / 204 columns); K = 256 (16 units).
+cudaError_t launch_pack_layer_T(const float* w, int k_valid, int n_in_stride, int n_valid, float scale,
+                                uint8_t* units_out, cudaStream_t stream);
 
 // ---- per-ray kernels (es_rays.cu)
 struct RayGeom {

@@ -73,6 +73,7 @@ struct RowState {
   float xc[3];   // canonical point (valid after the deform tail / = x without deform)
   float g[3];    // colour chain: canonical normal g_c
   float dc[3];   // colour chain: canonical view direction
+  float adj[4];  // reverse chains: (o.x, o.y, o.z, r) adjoint of this row's 3-wide output / sdf-row output
   long long pt;  // global point index (clamped to a valid one)
   bool valid;    // point index < n_points
   int s;         // tangent mode: 0 primal, 1..3 tangent wrt x_{s-1}; plain mode: 0
@@ -147,16 +148,41 @@ __device__ __forceinline__ void encode_part(float (&v)[PCOLS], const float (&pos
   });
 }
 
-// split v[PCOLS] into fp16 hi/lo and store as column part `part` of A ring slot `slot_base` for row `row`
-__device__ __forceinline__ void store_a_part(uint8_t* slot_base, int row, int part, const float (&v)[PCOLS]) {
+// split v[PCOLS] into fp16 hi/lo; store as column part `part` of A ring slot `slot_base` for row `row` (if non-null)
+// and/or dump the same hi/lo halves to global planes at dhi/dlo (pointers to this row's first column; training stash)
+__device__ __forceinline__ void emit_part(uint8_t* slot_base, int row, int part, const float (&v)[PCOLS],
+                                          uint16_t* dhi, uint16_t* dlo) {
 #pragma unroll
   for (int g = 0; g < PCOLS / 8; ++g) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], hi[j], lo[j]);
-    uint8_t* p = slot_base + ((PCOLS / 8) * part + g) * A_LBO + row * 16;
-    *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(p + SLOT_HALF_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (slot_base) {
+      uint8_t* p = slot_base + ((PCOLS / 8) * part + g) * A_LBO + row * 16;
+      *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(p + SLOT_HALF_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (dhi) {
+      *reinterpret_cast<uint4*>(dhi + 8 * g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(dlo + 8 * g) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+// read PCOLS values back from fp16 hi/lo planes (value = hi + lo)
+__device__ __forceinline__ void load_planes(const uint16_t* phi, const uint16_t* plo, float (&h)[PCOLS]) {
+#pragma unroll
+  for (int g = 0; g < PCOLS / 8; ++g) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(phi + 8 * g));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(plo + 8 * g));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[j]));
+      const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[j]));
+      h[8 * g + 2 * j] = fa.x + fb.x;
+      h[8 * g + 2 * j + 1] = fa.y + fb.y;
+    }
   }
 }
 
@@ -235,6 +261,48 @@ __device__ __forceinline__ void load_act(EpiCtx& c, int buf, int blk, const floa
   }
 }
 
+// raw accumulator columns (no bias / activation): reverse chains
+__device__ __forceinline__ void load_raw(EpiCtx& c, int buf, int blk, float (&v)[PCOLS]) {
+  const int col0 = 64 * blk + PCOLS * c.part;
+  tmem_ld<PCOLS>(c.tmem_base + (static_cast<uint32_t>(c.row & ~31) << 16) + buf * HID + col0, v);
+  tmem_ld_wait();
+}
+
+// Activation backward for the reverse (training) chains.  u = adjoint of the post-activation values of a forward
+// layer for this row; the forward stash holds those post-activation values h (primal rows) / hdot_j (tangent rows).
+//   relu     : zbar = [h_primal > 0] * u                                (all rows; relu'' = 0)
+//   softplus : sigma = 1 - exp(-100 h_primal)    (h = softplus(z)  =>  sigma(100 z) = 1 - exp(-100 h))
+//              tangent rows: zdotbar_j = sigma * u_j
+//              primal row  : zbar = sigma * u + 100 (1 - sigma) * sum_j hdot_j * u_j      (softplus'' = 100 s (1-s))
+template <bool TANGENT>
+__device__ __forceinline__ void bwd_gate(EpiCtx& c, const uint16_t* shi, const uint16_t* slo, int act, int s,
+                                         float (&u)[PCOLS]) {
+  float h[PCOLS];
+  load_planes(shi, slo, h);
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < PCOLS; ++i) {
+      const float hp = TANGENT ? __shfl_sync(0xffffffffu, h[i], c.lane & ~3) : h[i];
+      u[i] = hp > 0.f ? u[i] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < PCOLS; ++i) {
+      const float hp = TANGENT ? __shfl_sync(0xffffffffu, h[i], c.lane & ~3) : h[i];
+      const float e = __expf(-100.f * hp);  // 1 - sigma
+      if (TANGENT) {
+        float ct = (s > 0) ? h[i] * u[i] : 0.f;
+        ct += __shfl_xor_sync(0xffffffffu, ct, 1);
+        ct += __shfl_xor_sync(0xffffffffu, ct, 2);
+        const float su = (1.f - e) * u[i];
+        u[i] = (s == 0) ? fmaf(100.f * e, ct, su) : su;
+      } else {
+        u[i] = (1.f - e) * u[i];
+      }
+    }
+  }
+}
+
 template <bool TANGENT>
 __device__ __forceinline__ void load_act_dyn(EpiCtx& c, int act, int buf, int blk, const float* bias, int s,
                                              float (&v)[PCOLS]) {
@@ -277,13 +345,18 @@ __device__ __forceinline__ void release_d(EpiCtx& c, uint32_t g_layer) {
 // out = W_out . act(D + bias) summed over both column halves.  Returns the cross-half total in .x/.y/.z.
 template <int NOUT, bool TANGENT>
 __device__ __forceinline__ float4 tail_dot(EpiCtx& c, uint32_t g_layer, int act, const float* bias,
-                                           const float* w_out, int s) {
+                                           const float* w_out, int s, uint16_t* st_hi = nullptr,
+                                           uint16_t* st_lo = nullptr) {
   wait_d_full(c, g_layer);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
   for (int blk = 0; blk < 4; ++blk) {
     float v[PCOLS];
     load_act_dyn<TANGENT>(c, act, g_layer & 1, blk, bias, s, v);
+    if (st_hi) {  // training stash of the output layer's input (pointers address this row's column 0)
+      const int co = 64 * blk + PCOLS * c.part;
+      emit_part(nullptr, 0, 0, v, st_hi + co, st_lo + co);
+    }
     dot_accum<NOUT>(v, w_out, 64 * blk + PCOLS * c.part, acc);
   }
   release_d(c, g_layer);
@@ -300,7 +373,7 @@ __device__ __forceinline__ void encode_dispatch(EpiCtx& c, float (&v)[PCOLS], co
   });
 }
 
-template <int CHAIN, bool TANGENT, bool USE_DEFORM>
+template <int CHAIN, bool TANGENT, bool BWD>
 __global__ void __launch_bounds__(N_THREADS, 1)
 mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__ ChainIO io) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -461,7 +534,15 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         rs.t = 0.f;
         rs.g[0] = rs.g[1] = rs.g[2] = 0.f;
         rs.dc[0] = rs.dc[1] = rs.dc[2] = 0.f;
-        if constexpr (CHAIN == CHAIN_COLOR) {
+        rs.adj[0] = rs.adj[1] = rs.adj[2] = rs.adj[3] = 0.f;
+        if constexpr (BWD) {
+          rs.x[0] = rs.x[1] = rs.x[2] = 0.f;
+          rs.xc[0] = rs.xc[1] = rs.xc[2] = 0.f;
+          if (rs.valid) {  // padding rows carry zero adjoints so they add nothing to the weight gradients
+            const float4 a = __ldg(reinterpret_cast<const float4*>(io.adj) + (TANGENT ? rs.pt * 4 + rs.s : rs.pt));
+            rs.adj[0] = a.x; rs.adj[1] = a.y; rs.adj[2] = a.z; rs.adj[3] = a.w;
+          }
+        } else if constexpr (CHAIN == CHAIN_COLOR) {
           const float* xc = io.x_c + rs.pt * 3;
           const float* gc = io.g_c + rs.pt * 3;
           const float* J = io.jac + rs.pt * 9;
@@ -491,6 +572,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         }
       }
       float sdf_acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const size_t row_global = static_cast<size_t>(tile) * TILE_ROWS + c.row;  // stash row
 
       for (int l = 0; l < prog.n_layers; ++l, ++c.g) {
         const LayerProg& L = prog.layer[l];
@@ -500,7 +582,10 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
 
         if (L.pre_op == PRE_DEFORM_TAIL) {
           // deform output layer (3 x 256, fp32 FFMA) -> x_c = x + delta ; tangent rows give dDelta/dx_{s-1}
-          float4 r = tail_dot<3, TANGENT>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, rs.s);
+          // training: the output layer's input goes to stash slot l (this layer has no SRC_PREV chunk of its own)
+          uint16_t* sh = io.stash_hi ? io.stash_hi + (static_cast<size_t>(l) * io.stash_rows + row_global) * HID : nullptr;
+          uint16_t* sl = io.stash_hi ? io.stash_lo + (static_cast<size_t>(l) * io.stash_rows + row_global) * HID : nullptr;
+          float4 r = tail_dot<3, TANGENT>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, rs.s, sh, sl);
           float dl[3] = {r.x, r.y, r.z};
           if (!TANGENT) {
 #pragma unroll
@@ -527,7 +612,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         }
 
         int n_prev_left = 0;
-        for (int ck = 0; ck < L.n_chunks; ++ck) n_prev_left += (L.src[ck] == SRC_PREV);
+        for (int ck = 0; ck < L.n_chunks; ++ck) n_prev_left += (L.src[ck] == SRC_PREV || L.src[ck] == SRC_BWD_PREV);
 
         for (int ck = 0; ck < L.n_chunks; ++ck, ++c.ac) {
           const uint32_t slot = c.ac % NSLOT;
@@ -536,14 +621,57 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           float v[PCOLS];
           const int src = L.src[ck];
           bool active = true;
-          if (src == SRC_PREV) {
+          uint16_t* dump_hi = nullptr;
+          uint16_t* dump_lo = nullptr;
+          const int col0 = 64 * L.arg[ck] + PCOLS * c.part;
+          if (BWD && (src == SRC_BWD_PREV || src == SRC_BWD_OUTER3)) {
+            if (src == SRC_BWD_PREV) {
+              if (!prev_waited) {
+                wait_d_full(c, c.g - 1);
+                prev_waited = true;
+              }
+              load_raw(c, (c.g - 1) & 1, L.arg[ck], v);
+              if (L.rank1) {
+#pragma unroll
+                for (int i = 0; i < PCOLS; ++i) v[i] = fmaf(rs.adj[3], __ldg(prog.sdf_out_w + col0 + i), v[i]);
+              }
+              if (--n_prev_left == 0) release_d(c, c.g - 1);
+            } else {
+#pragma unroll
+              for (int i = 0; i < PCOLS; ++i)
+                v[i] = rs.adj[0] * __ldg(prog.outer3_w + col0 + i) + rs.adj[1] * __ldg(prog.outer3_w + HID + col0 + i) +
+                       rs.adj[2] * __ldg(prog.outer3_w + 2 * HID + col0 + i);
+            }
+            const size_t so = (static_cast<size_t>(L.stash_slot) * io.stash_rows + row_global) * HID + col0;
+            bwd_gate<TANGENT>(c, io.stash_hi + so, io.stash_lo + so, L.bwd_act, rs.s, v);
+            const size_t zo = (static_cast<size_t>(L.zbar_slot) * io.stash_rows + row_global) * HID + col0;
+            dump_hi = io.zbar_hi + zo;
+            dump_lo = io.zbar_lo + zo;
+          } else if (BWD && src == SRC_ADJ_FEAT) {
+            if (rs.valid && rs.s == 0) {
+              const float4* f4 = reinterpret_cast<const float4*>(io.adj_feat + rs.pt * HID + col0);
+#pragma unroll
+              for (int q = 0; q < PCOLS / 4; ++q) {
+                float4 f = __ldg(f4 + q);
+                v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < PCOLS; ++i) v[i] = 0.f;
+            }
+          } else if (src == SRC_PREV) {
             if (!prev_waited) {
               wait_d_full(c, c.g - 1);
               prev_waited = true;
             }
             load_act_dyn<TANGENT>(c, act_prev, (c.g - 1) & 1, L.arg[ck], bias_prev, rs.s, v);
-            if (L.side_dot) dot_accum<1>(v, prog.sdf_out_w, 64 * L.arg[ck] + PCOLS * c.part, sdf_acc);
+            if (L.side_dot) dot_accum<1>(v, prog.sdf_out_w, col0, sdf_acc);
             if (--n_prev_left == 0) release_d(c, c.g - 1);
+            if (io.stash_hi) {  // training: keep this layer's input for the reverse pass / weight gradients
+              const size_t so = (static_cast<size_t>(l) * io.stash_rows + row_global) * HID + col0;
+              dump_hi = io.stash_hi + so;
+              dump_lo = io.stash_lo + so;
+            }
           } else if (src == SRC_ENC_DEFORM) {
             encode_dispatch<SRC_ENC_DEFORM, TANGENT>(c, v, rs.x, rs);
           } else if (src == SRC_ENC_SDF) {
@@ -562,7 +690,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
               v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
             }
           }
-          if (active && !(io.debug_flags & 2)) store_a_part(slot_base, c.row, c.part, v);
+          if (active) emit_part((io.debug_flags & 2) ? nullptr : slot_base, c.row, c.part, v, dump_hi, dump_lo);
           fence_proxy_async_smem();
           mbar_arrive(&bars.a_full[slot]);
           if (c.tr) trace_ev(io.trace, 5000 + l * 16 + ck);  // EPI: chunk ck of layer l written
@@ -594,8 +722,23 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
             io.out_gc[rs.pt * 3 + (rs.s - 1)] = r.x;
           }
         }
+      } else if (BWD && prog.post_op == POST_BWD_DUMP) {
+        wait_d_full(c, c.g - 1);
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk) {
+          float v[PCOLS];
+          const int col0 = 64 * blk + PCOLS * c.part;
+          load_raw(c, (c.g - 1) & 1, blk, v);
+          const size_t so = (static_cast<size_t>(prog.post_stash_slot) * io.stash_rows + row_global) * HID + col0;
+          bwd_gate<TANGENT>(c, io.stash_hi + so, io.stash_lo + so, prog.post_bwd_act, rs.s, v);
+          const size_t zo = (static_cast<size_t>(prog.post_zbar_slot) * io.stash_rows + row_global) * HID + col0;
+          emit_part(nullptr, 0, 0, v, io.zbar_hi + zo, io.zbar_lo + zo);
+        }
+        release_d(c, c.g - 1);
       } else if (prog.post_op == POST_COLOR_TAIL) {
-        float4 r = tail_dot<3, false>(c, c.g - 1, act_last, bias_last, prog.color_out_w, 0);
+        uint16_t* sh = io.stash_hi ? io.stash_hi + (static_cast<size_t>(prog.n_layers) * io.stash_rows + row_global) * HID : nullptr;
+        uint16_t* sl = io.stash_hi ? io.stash_lo + (static_cast<size_t>(prog.n_layers) * io.stash_rows + row_global) * HID : nullptr;
+        float4 r = tail_dot<3, false>(c, c.g - 1, act_last, bias_last, prog.color_out_w, 0, sh, sl);
         if (c.part == 0 && rs.valid) {
           float o[3] = {r.x, r.y, r.z};
 #pragma unroll
@@ -630,9 +773,9 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-template <int CHAIN, bool TANGENT, bool USE_DEFORM>
+template <int CHAIN, bool TANGENT, bool BWD>
 static cudaError_t launch_one(const ChainProg& prog, const ChainIO& io, int n_sms, cudaStream_t stream) {
-  auto kern = mlp_chain_kernel<CHAIN, TANGENT, USE_DEFORM>;
+  auto kern = mlp_chain_kernel<CHAIN, TANGENT, BWD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
   if (e != cudaSuccess) return e;
   const int pts_per_tile = TANGENT ? TILE_ROWS / 4 : TILE_ROWS;
@@ -644,13 +787,15 @@ static cudaError_t launch_one(const ChainProg& prog, const ChainIO& io, int n_sm
 }
 
 cudaError_t launch_mlp_chain(int chain, bool tangent, bool use_deform, const ChainProg& prog, const ChainIO& io,
-                             int n_sms, cudaStream_t stream) {
-  if (chain == CHAIN_COLOR) return launch_one<CHAIN_COLOR, false, true>(prog, io, n_sms, stream);
+                             int n_sms, cudaStream_t stream, bool bwd) {
+  (void)use_deform;  // the layer program already encodes whether a deformation network is present
+  if (chain == CHAIN_COLOR)
+    return bwd ? launch_one<CHAIN_COLOR, false, true>(prog, io, n_sms, stream)
+               : launch_one<CHAIN_COLOR, false, false>(prog, io, n_sms, stream);
   if (chain == CHAIN_SDF) {
-    if (tangent) return use_deform ? launch_one<CHAIN_SDF, true, true>(prog, io, n_sms, stream)
-                                   : launch_one<CHAIN_SDF, true, false>(prog, io, n_sms, stream);
-    return use_deform ? launch_one<CHAIN_SDF, false, true>(prog, io, n_sms, stream)
-                      : launch_one<CHAIN_SDF, false, false>(prog, io, n_sms, stream);
+    if (bwd) return tangent ? launch_one<CHAIN_SDF, true, true>(prog, io, n_sms, stream) : cudaErrorInvalidValue;
+    return tangent ? launch_one<CHAIN_SDF, true, false>(prog, io, n_sms, stream)
+                   : launch_one<CHAIN_SDF, false, false>(prog, io, n_sms, stream);
   }
   return cudaErrorInvalidValue;
 }

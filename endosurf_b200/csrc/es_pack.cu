@@ -28,6 +28,34 @@ __global__ void pack_layer_kernel(const float* __restrict__ w, int n_out, int n_
   *reinterpret_cast<uint4*>(p + UNIT_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+__global__ void pack_layer_T_kernel(const float* __restrict__ w, int k_valid, int n_in_stride, int n_valid,
+                                    float scale, uint8_t* __restrict__ units) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (sb, kg, n) over K = 256
+  if (idx >= (HID / SUB_K) * 4 * HID) return;
+  const int n = idx % HID;
+  const int kg = (idx / HID) % 4;
+  const int sb = idx / (4 * HID);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = sb * SUB_K + kg * 8 + j;
+    v[j] = (k < k_valid && n < n_valid) ? w[static_cast<size_t>(k) * n_in_stride + n] * scale : 0.f;
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+  uint8_t* p = units + static_cast<size_t>(2 * sb) * UNIT_BYTES + kg * B_LBO + n * 16;
+  *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(p + UNIT_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+cudaError_t launch_pack_layer_T(const float* w, int k_valid, int n_in_stride, int n_valid, float scale,
+                                uint8_t* units_out, cudaStream_t stream) {
+  const int total = (HID / SUB_K) * 4 * HID;
+  pack_layer_T_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, k_valid, n_in_stride, n_valid, scale, units_out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_layer(const float* w, int n_out, int n_in, const int* colmap_dev, int k_total, float scale,
                               uint8_t* units_out, cudaStream_t stream) {
   const int total = (k_total / SUB_K) * 4 * HID;

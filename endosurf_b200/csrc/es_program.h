@@ -32,10 +32,14 @@ enum : uint8_t {
   SRC_COLOR_A,      // colour-net input, first 64 of [enc10(x_c), g_c, enc4(d_c)] in kernel order
   SRC_COLOR_B,      // remaining 30 (one 32-wide sub-block)
   SRC_FEAT,         // geo_feat[:, 64*arg .. +64) read from global memory
+  // reverse (training) chains: the "activations" are adjoints, the weights are packed transposed
+  SRC_ADJ_FEAT,     // d loss / d feat [P,256] (primal rows; tangent rows are zero)
+  SRC_BWD_PREV,     // activation-backward of the previous reverse layer's accumulator using the forward stash
+  SRC_BWD_OUTER3,   // same, but the incoming adjoint is adj.xyz . W_out (the 3-wide output layer, no MMA)
 };
 enum : uint8_t { ACT_NONE = 0, ACT_RELU = 1, ACT_SOFTPLUS100 = 2 };
 enum : uint8_t { PRE_NONE = 0, PRE_DEFORM_TAIL = 1 };
-enum : uint8_t { POST_NONE = 0, POST_SDF_TAIL = 1, POST_FEAT_OUT = 2, POST_COLOR_TAIL = 3 };
+enum : uint8_t { POST_NONE = 0, POST_SDF_TAIL = 1, POST_FEAT_OUT = 2, POST_COLOR_TAIL = 3, POST_BWD_DUMP = 4 };
 
 struct LayerProg {
   uint8_t n_chunks;
@@ -45,6 +49,11 @@ struct LayerProg {
   uint8_t src[MAXC];
   uint8_t arg[MAXC];
   uint8_t nsub[MAXC];  // number of 32-wide K sub-blocks in the chunk that carry weights (1 or 2)
+  // reverse chains only
+  uint8_t stash_slot;  // forward stash slot holding the activations whose derivative gates this layer's input
+  uint8_t zbar_slot;   // where this layer's input (adjoint of a forward pre-activation) is dumped for the weight grads
+  uint8_t bwd_act;     // activation being differentiated (ACT_RELU / ACT_SOFTPLUS100)
+  uint8_t rank1;       // 1: add adj.w * sdf_out_w[col] to the incoming adjoint (sdf row of the output layer)
 };
 
 struct ChainProg {
@@ -62,6 +71,9 @@ struct ChainProg {
   const float* feat_out_b;    // [256]     (sdf last layer rows 1..256 bias)
   const float* color_out_w;   // [3][256]
   const float* color_out_b;   // [3]
+  const float* outer3_w;      // reverse chains: [3][256] output-layer weights for SRC_BWD_OUTER3
+  // POST_BWD_DUMP: last activation-backward of a reverse chain (its result feeds no MMA, only the weight grads)
+  int32_t post_stash_slot, post_zbar_slot, post_bwd_act;
 };
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -273,6 +273,79 @@ class EndoSurfRenderer(nn.Module):
             self._consts[key] = fn()
         return self._consts[key]
 
+    # ------------------------------------------------------------------ differentiable (training) path
+    train_ray_chunk = 1024  # rays per autograd.Function call: bounds the activation stash (about 10 GiB per chunk)
+
+    def point_field(self, x, d, t):
+        """Differentiable EndoSurfNet.forward + gradient queries on explicit points:
+        (sdf [n,1], g_c [n,3], jac [n,3,3], rgb [n,3]); gradients flow to every network parameter."""
+        from .training import PointFieldFn, effective_weights
+        return PointFieldFn.apply(self, x, d, t, *effective_weights(self.model))
+
+    def _sample_z(self, rays, iter_step, perturb_overwrite):
+        """Coarse + hierarchical sampling only (no grad, CUDA): z_vals [R,M]."""
+        self._sync_weights()
+        lib, ctx = _lib.load(), self._context()
+        dev, R = rays.device, rays.shape[0]
+        ns, ni = int(self.n_samples), int(self.n_importance)
+        perturb = self.perturb if perturb_overwrite is None else perturb_overwrite
+        do_up = bool(iter_step >= self.important_begin_iter and ni > 0)
+        M = ns + (ni if do_up else 0)
+        steps = int(self.up_sample_steps)
+        t_vals = self._const(("t", ns, dev), lambda: torch.linspace(0.0, 1.0, ns, device=dev))
+        u_vals = None
+        if do_up:
+            k = ni // steps
+            u_vals = self._const(("u", k, dev),
+                                 lambda: torch.linspace(0.0 + 0.5 / k, 1.0 - 0.5 / k, steps=k, device=dev))
+        t_rand = (torch.rand([R, 1], device=dev) - 0.5).reshape(-1).contiguous() if perturb else None
+        z = torch.empty(R, M, device=dev)
+        prm = _lib.EsRenderParams(
+            n_samples=ns, n_importance=ni, up_sample_steps=steps, do_upsample=int(do_up), cos_anneal_ratio=0.0,
+            variance=self.model.deviation_network.variance.data_ptr(), t_vals=t_vals.data_ptr(),
+            u_vals=u_vals.data_ptr() if u_vals is not None else None,
+            t_rand=t_rand.data_ptr() if t_rand is not None else None, z_override=None)
+        o = _lib.EsRenderOut(z_vals=z.data_ptr())
+        _lib.check(ctx, lib.es_render_rays(ctx, _ptr(rays), R, C.byref(prm), C.byref(o), self._stream()),
+                   "es_render_rays(sampling)")
+        return z
+
+    def _render_rays_train(self, rays, iter_step, perturb_overwrite, z_vals_override=None):
+        """render_rays with autograd (endosurf.py:60-213): sampling runs without grad exactly as in the reference
+        (:86), the sample-point pipeline is the fused CUDA forward/backward (training.PointFieldFn), compositing
+        is differentiable PyTorch on [R,M] tensors."""
+        from .training import composite
+        rays = rays.detach().contiguous().float()
+        R = rays.shape[0]
+        with torch.no_grad():
+            z = z_vals_override.detach().float() if z_vals_override is not None else \
+                self._sample_z(rays, iter_step, perturb_overwrite)
+        M = z.shape[1]
+        sample_dist = 2.0 / self.n_samples
+        rays_o, rays_d, time = rays[:, :3], rays[:, 3:6], rays[:, 8]
+        d_z = rays_d / (rays_d[:, 2:] + 1e-6)
+        dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((R, 1), sample_dist, device=z.device)], -1)
+        mid_z = z + dists * 0.5
+        pts = rays_o[:, None, :] + d_z[:, None, :] * mid_z[..., None]
+        sdf_l, go_l, rgb_l = [], [], []
+        for r0 in range(0, R, self.train_ray_chunk):
+            r1 = min(R, r0 + self.train_ray_chunk)
+            n = (r1 - r0) * M
+            x = pts[r0:r1].reshape(n, 3)
+            dd = rays_d[r0:r1, None, :].expand(r1 - r0, M, 3).reshape(n, 3)
+            tt = time[r0:r1, None].expand(r1 - r0, M).reshape(n, 1)
+            sdf, g_c, jac, rgb = self.point_field(x, dd, tt)
+            g_o = torch.einsum("nij,ni->nj", jac, g_c)  # = autograd normal in observed space (SURVEY 7.4)
+            sdf_l.append(sdf.reshape(r1 - r0, M))
+            go_l.append(g_o.reshape(r1 - r0, M, 3))
+            rgb_l.append(rgb.reshape(r1 - r0, M, 3))
+        inv_s = torch.exp(self.model.deviation_network.variance * 10.0).clip(1e-6, 1e6)
+        out = composite(torch.cat(sdf_l), torch.cat(go_l), torch.cat(rgb_l), rays_d, pts, z, sample_dist, inv_s,
+                        self.get_cos_anneal_ratio(iter_step))
+        out["weight_max"] = torch.max(out["weights"], dim=-1, keepdim=True)[0]
+        out["s_val"] = (1.0 / inv_s).expand(R, M).mean(dim=-1, keepdim=True)
+        return out
+
     def sync_check(self):
         """Synchronise and raise if any kernel tripped its device-side watchdog (tests / debugging)."""
         lib, ctx = _lib.load(), self._context()
@@ -348,9 +421,7 @@ class EndoSurfRenderer(nn.Module):
                     return_extras=False, **kwargs):
         """EndoSurfRenderer.render_rays (endosurf.py:60-132): rays [R,9] -> the reference's 8-key dict."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
-            raise NotImplementedError(
-                "the differentiable (training) render_rays path of endosurf_b200 is not built yet; call under "
-                "torch.no_grad() for the forward path (DESIGN.md, 'what comes next')")
+            return self._render_rays_train(rays, iter_step, perturb_overwrite, z_vals_override)
         self._sync_weights()
         lib, ctx = _lib.load(), self._context()
         rays = rays.detach().contiguous().float()

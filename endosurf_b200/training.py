@@ -1,0 +1,306 @@
+"""Differentiable (training) point pipeline on top of the fused sm_100a chains.
+
+The reference differentiates ``EndoSurfNet.forward`` with ``torch.autograd`` (``create_graph=True`` at
+``src/renderer/endosurf.py:594-658``).  Here :class:`PointFieldFn` is a custom ``autograd.Function``:
+
+* forward  = ``es_point_forward_train``: the same fused tcgen05 kernels as inference, additionally keeping every MMA
+  layer's input rows (primal + 3 forward-mode tangent rows per point) as fp16 hi/lo planes (the "stash");
+* backward = three fused reverse chains (``es_point_backward``: colour, sdf, deform) that push the output adjoints
+  through the transposed weights on the tensor cores, gate them with the stashed activations (ReLU mask / softplus'
+  and softplus'' cross terms of the tangent rows) and write the adjoint of every forward pre-activation ("zbar").
+  Weight gradients are then plain ``zbar^T @ stash`` GEMMs (library GEMMs on the stashed planes), and the adjoints of
+  the small per-point quantities (positional encodings, J d normalisation) are closed-form elementwise PyTorch.
+
+Gradients are returned with respect to the *effective* weights ``W = g v/||v||`` and biases; PyTorch's own autograd
+carries them on to ``weight_g`` / ``weight_v`` (the weight-norm fold is differentiable plumbing, reference
+utils.py:57-58).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List
+
+import torch
+
+from . import _lib
+
+SQRT2 = math.sqrt(2.0)
+
+
+# ------------------------------------------------------------------------------------------------ small torch helpers
+def freq_enc(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
+    """[x, sin(2^k x), cos(2^k x)]_k in the reference's column order (encoder.py:40-54)."""
+    out = [x]
+    for k in range(n_freqs):
+        f = float(2.0 ** k)
+        out += [torch.sin(x * f), torch.cos(x * f)]
+    return torch.cat(out, -1)
+
+
+def freq_enc_tangent(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
+    """d enc(x) / d x_j for j = 0..2  ->  [n, 3, 3(2L+1)] (what the kernels feed to the tangent rows)."""
+    n, dim = x.shape
+    cols = [torch.ones_like(x)]
+    for k in range(n_freqs):
+        f = float(2.0 ** k)
+        cols += [f * torch.cos(x * f), -f * torch.sin(x * f)]
+    dfull = torch.cat(cols, -1)  # derivative of every column wrt its own component
+    comp = (torch.arange(dfull.shape[1], device=x.device) % dim)
+    sel = torch.stack([(comp == j) for j in range(dim)], 0).to(x.dtype)  # [3, width]
+    return dfull[:, None, :] * sel[None, :, :]
+
+
+def planes_f32(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
+    return hi.view(torch.float16).float() + lo.view(torch.float16).float()
+
+
+def _pow2_scale(*tensors) -> torch.Tensor:
+    """Power-of-two loss scale so that the largest adjoint entering a reverse chain is ~16 (fp16 hi/lo planes keep
+    22 bits relative to that; no host sync)."""
+    amax = torch.stack([t.detach().abs().max() for t in tensors if t is not None and t.numel() > 0]).max()
+    amax = torch.where(amax > 0, amax, torch.ones_like(amax))
+    return torch.exp2(torch.floor(torch.log2(16.0 / amax)))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class PointFieldFn(torch.autograd.Function):
+    """(x, d, t, effective weights...) -> (sdf [n,1], g_c [n,3], jac [n,3,3], rgb [n,3])."""
+
+    @staticmethod
+    def forward(ctx, renderer, x, d, t, *wb):
+        lib, ectx = _lib.load(), renderer._context()
+        stream = renderer._stream()
+        n = x.shape[0]
+        dev = x.device
+        use_deform = renderer.model.use_deform
+        L = renderer._cfg_struct.n_layers
+        nets = ([0] if use_deform else []) + [1, 2]
+        # unpack [W_0..W_{L-1}, b_0..b_{L-1}] per network and upload (packs forward + transposed units)
+        ws, bs, k = {}, {}, 0
+        for net in nets:
+            ws[net] = [w.detach().contiguous() for w in wb[k:k + L]]
+            bs[net] = [b.detach().contiguous() for b in wb[k + L:k + 2 * L]]
+            k += 2 * L
+            wp = (C.c_void_p * L)(*[w.data_ptr() for w in ws[net]])
+            bp = (C.c_void_p * L)(*[b.data_ptr() for b in bs[net]])
+            _lib.check(ectx, lib.es_load_network(ectx, net, wp, bp, stream), "es_load_network")
+        renderer._packed_version = None  # the context now holds these weights, not necessarily the module's
+        lay = (C.c_int64 * 6)()
+        _lib.check(ectx, lib.es_train_layout(ectx, n, lay), "es_train_layout")
+        g_rows, g_slots, c_rows, c_slots, z_slots, sdf_off = [int(v) for v in lay]
+        gs_hi = torch.empty(g_slots, g_rows, 256, dtype=torch.int16, device=dev)
+        gs_lo = torch.empty_like(gs_hi)
+        cs_hi = torch.empty(c_slots, c_rows, 256, dtype=torch.int16, device=dev)
+        cs_lo = torch.empty_like(cs_hi)
+        x = x.detach().contiguous().float()
+        d = d.detach().contiguous().float()
+        t = t.detach().reshape(-1).contiguous().float()
+        x_c = torch.empty(n, 3, device=dev)
+        jac = torch.empty(n, 3, 3, device=dev)
+        sdf = torch.empty(n, 1, device=dev)
+        g_c = torch.empty(n, 3, device=dev)
+        feat = torch.empty(n, 256, device=dev)
+        rgb = torch.empty(n, 3, device=dev)
+        rc = lib.es_point_forward_train(ectx, _ptr(x), _ptr(t), 1, 1, _ptr(d), 1, 3, n, _ptr(x_c),
+                                        _ptr(jac if use_deform else None), _ptr(sdf),
+                                        _ptr(g_c), _ptr(feat), _ptr(rgb), _ptr(gs_hi), _ptr(gs_lo), _ptr(cs_hi),
+                                        _ptr(cs_lo), stream)
+        _lib.check(ectx, rc, "es_point_forward_train")
+        if not use_deform:
+            jac = torch.eye(3, device=dev).expand(n, 3, 3).contiguous()
+        ctx.renderer = renderer
+        ctx.meta = (n, L, use_deform, nets, g_rows, g_slots, c_rows, c_slots, z_slots, sdf_off)
+        ctx.ws, ctx.bs = ws, bs
+        ctx.save_for_backward(x, d, t, x_c, jac, g_c, feat, rgb, gs_hi, gs_lo, cs_hi, cs_lo)
+        return sdf, g_c, jac, rgb
+
+    @staticmethod
+    def backward(ctx, sdf_bar, gc_bar, jac_bar, rgb_bar):
+        renderer = ctx.renderer
+        lib, ectx = _lib.load(), renderer._context()
+        stream = renderer._stream()
+        n, L, use_deform, nets, g_rows, g_slots, c_rows, c_slots, z_slots, sdf_off = ctx.meta
+        x, d, t, x_c, jac, g_c, feat, rgb, gs_hi, gs_lo, cs_hi, cs_lo = ctx.saved_tensors
+        dev = x.device
+        ws, bs = ctx.ws, ctx.bs
+        cfg = renderer._cfg_struct
+        skip = cfg.skip_layer
+        # the context may have been re-packed by another forward since; make sure it holds THIS call's weights
+        for net in nets:
+            wp = (C.c_void_p * L)(*[w.data_ptr() for w in ws[net]])
+            bp = (C.c_void_p * L)(*[b.data_ptr() for b in bs[net]])
+            _lib.check(ectx, lib.es_load_network(ectx, net, wp, bp, stream), "es_load_network")
+        renderer._packed_version = None
+
+        def zeros_like_or(tns, shape):
+            return tns if tns is not None else torch.zeros(shape, device=dev)
+
+        sdf_bar = zeros_like_or(sdf_bar, (n, 1)).float()
+        gc_bar = zeros_like_or(gc_bar, (n, 3)).float()
+        jac_bar = zeros_like_or(jac_bar, (n, 3, 3)).float()
+        rgb_bar = zeros_like_or(rgb_bar, (n, 3)).float()
+        gw = {net: [None] * L for net in nets}
+        gb = {net: [None] * L for net in nets}
+        p_g = g_rows // 4  # padded point count of the geometry chains
+
+        def run_reverse(net, adj, adj_feat, stash_hi, stash_lo, rows):
+            zb_hi = torch.empty(z_slots, rows, 256, dtype=torch.int16, device=dev)
+            zb_lo = torch.empty_like(zb_hi)
+            rc = lib.es_point_backward(ectx, net, n, _ptr(stash_hi), _ptr(stash_lo), _ptr(adj), _ptr(adj_feat),
+                                       _ptr(zb_hi), _ptr(zb_lo), stream)
+            _lib.check(ectx, rc, "es_point_backward")
+            return zb_hi, zb_lo
+
+        # ============================================================== colour network
+        d_c_u = torch.bmm(jac, d.unsqueeze(-1)).squeeze(-1)
+        d_c = d_c_u / (torch.linalg.norm(d_c_u, dim=-1, keepdim=True) + 1e-10)
+        inp_c = torch.cat([freq_enc(x_c, cfg.multires_color_pos), g_c, freq_enc(d_c, cfg.multires_color_dir), feat], -1)
+        o_c = rgb_bar * rgb * (1.0 - rgb)                     # through the output sigmoid (endosurf.py:841)
+        s_c = _pow2_scale(o_c)
+        adj_c = torch.cat([o_c * s_c, torch.zeros(n, 1, device=dev)], -1).contiguous()
+        zc_hi, zc_lo = run_reverse(2, adj_c, None, cs_hi, cs_lo, c_rows)
+        Wc = ws[2]
+        zbar = lambda hi, lo, m, s: planes_f32(hi[m], lo[m]) / s
+        Z0 = zbar(zc_hi, zc_lo, 0, s_c)
+        inp_bar = Z0[:n] @ Wc[0]
+        gw[2][0] = Z0[:n].t() @ inp_c
+        gb[2][0] = Z0.sum(0)
+        for m in range(1, L - 1):
+            Zm = zbar(zc_hi, zc_lo, m, s_c)
+            Hm = planes_f32(cs_hi[m], cs_lo[m])
+            g = Zm.t() @ Hm
+            if m == skip:
+                inp_bar = inp_bar + Zm[:n] @ (Wc[m][:, 256:] / SQRT2)
+                g = torch.cat([g, Zm[:n].t() @ inp_c], 1) / SQRT2
+            gw[2][m] = g
+            gb[2][m] = Zm.sum(0)
+        H_out = planes_f32(cs_hi[L - 1], cs_lo[L - 1])[:n]
+        gw[2][L - 1] = o_c.t() @ H_out
+        gb[2][L - 1] = o_c.sum(0)
+        nx = 3 * (1 + 2 * cfg.multires_color_pos)
+        nd = 3 * (1 + 2 * cfg.multires_color_dir)
+        ex_bar, gc_col_bar, ed_bar, feat_bar = inp_bar[:, :nx], inp_bar[:, nx:nx + 3], \
+            inp_bar[:, nx + 3:nx + 3 + nd], inp_bar[:, nx + 3 + nd:]
+        # adjoints of x_c (through enc10) and of J (through d_c = normalize(J d)): tiny elementwise graphs
+        with torch.enable_grad():
+            xc_r = x_c.detach().requires_grad_(True)
+            j_r = jac.detach().requires_grad_(True)
+            u = torch.bmm(j_r, d.unsqueeze(-1)).squeeze(-1)
+            dcr = u / (torch.linalg.norm(u, dim=-1, keepdim=True) + 1e-10)
+            obj = (freq_enc(xc_r, cfg.multires_color_pos) * ex_bar).sum() + \
+                (freq_enc(dcr, cfg.multires_color_dir) * ed_bar).sum()
+            xc_bar, jbar_color = torch.autograd.grad(obj, [xc_r, j_r])
+
+        # ============================================================== sdf network
+        gc_tot = gc_bar + gc_col_bar
+        adj_s = torch.zeros(p_g, 4, 4, device=dev)
+        s_s = _pow2_scale(sdf_bar, gc_tot, feat_bar)
+        adj_s[:n, 0, 3] = sdf_bar[:, 0] * s_s
+        adj_s[:n, 1:, 3] = gc_tot * s_s
+        feat_bar_s = (feat_bar * s_s).contiguous()
+        zs_hi, zs_lo = run_reverse(1, adj_s, feat_bar_s, gs_hi, gs_lo, g_rows)
+        Ws = ws[1]
+        with torch.enable_grad():
+            xc_r = x_c.detach().requires_grad_(True)
+            e0 = freq_enc(xc_r, cfg.multires_sdf_pos)                     # [n, 39]
+            et = freq_enc_tangent(xc_r, cfg.multires_sdf_pos)             # [n, 3, 39]
+            a0 = torch.cat([e0[:, None, :], et], 1)                       # rows of the first sdf layer [n,4,39]
+            Z0 = zbar(zs_hi, zs_lo, 0, s_s).view(p_g, 4, 256)[:n]
+            E = Z0 @ Ws[0]                                                # adjoint of those rows [n,4,39]
+            gw[1][0] = Z0.reshape(-1, 256).t() @ a0.detach().reshape(-1, a0.shape[-1])
+            gb[1][0] = Z0[:, 0].sum(0)
+            for m in range(1, L - 1):
+                Zm = zbar(zs_hi, zs_lo, m, s_s)
+                Hm = planes_f32(gs_hi[sdf_off + m], gs_lo[sdf_off + m])
+                g = Zm.t() @ Hm
+                Zp = Zm.view(p_g, 4, 256)[:n]
+                if m == skip:
+                    E = E + Zp @ (Ws[m][:, 256:] / SQRT2)
+                    g = torch.cat([g, Zp.reshape(-1, 256).t() @ a0.detach().reshape(-1, a0.shape[-1])], 1) / SQRT2
+                gw[1][m] = g
+                gb[1][m] = Zp[:, 0].sum(0)
+            xc_bar = xc_bar + torch.autograd.grad((a0 * E.detach()).sum(), xc_r)[0]
+        H8 = planes_f32(gs_hi[sdf_off + L - 1], gs_lo[sdf_off + L - 1]).view(p_g, 4, 256)[:n]
+        r_rows = torch.cat([sdf_bar, gc_tot], 1)                          # [n,4]: adjoint of the sdf-row output
+        g_row0 = (r_rows.reshape(-1, 1) * H8.reshape(-1, 256)).sum(0, keepdim=True)
+        gw[1][L - 1] = torch.cat([g_row0, feat_bar.t() @ H8[:, 0]], 0)
+        gb[1][L - 1] = torch.cat([sdf_bar.sum(0), feat_bar.sum(0)], 0)
+
+        # ============================================================== deformation network
+        if use_deform:
+            jbar = jac_bar + jbar_color
+            adj_d = torch.zeros(p_g, 4, 4, device=dev)
+            s_d = _pow2_scale(xc_bar, jbar)
+            adj_d[:n, 0, :3] = xc_bar * s_d
+            adj_d[:n, 1:, :3] = jbar.permute(0, 2, 1) * s_d              # tangent row j carries d/d(dx_c_i/dx_j)
+            zd_hi, zd_lo = run_reverse(0, adj_d, None, gs_hi, gs_lo, g_rows)
+            Wd = ws[0]
+            out_dims = [w.shape[0] for w in Wd]
+            ex = freq_enc(x, cfg.multires_deform_pos)
+            etx = freq_enc_tangent(x, cfg.multires_deform_pos)
+            tt = freq_enc(t.reshape(-1, 1), cfg.multires_deform_time)
+            a0 = torch.cat([torch.cat([ex, tt], -1)[:, None, :],
+                            torch.cat([etx, torch.zeros(n, 3, tt.shape[1], device=dev)], -1)], 1)  # [n,4,52]
+            Z0 = zbar(zd_hi, zd_lo, 0, s_d).view(p_g, 4, 256)[:n]
+            gw[0][0] = Z0.reshape(-1, 256).t() @ a0.reshape(-1, a0.shape[-1])
+            gb[0][0] = Z0[:, 0].sum(0)
+            for m in range(1, L - 1):
+                Zm = zbar(zd_hi, zd_lo, m, s_d)
+                Hm = planes_f32(gs_hi[m], gs_lo[m])
+                g = (Zm.t() @ Hm)[:out_dims[m]]
+                Zp = Zm.view(p_g, 4, 256)[:n]
+                if m == skip:
+                    hprev = out_dims[m - 1]
+                    g = torch.cat([g[:, :hprev], (Zp.reshape(-1, 256).t() @ a0.reshape(-1, a0.shape[-1]))[:out_dims[m]]],
+                                  1) / SQRT2
+                gw[0][m] = g
+                gb[0][m] = Zp[:, 0].sum(0)[:out_dims[m]]
+            H8 = planes_f32(gs_hi[L - 1], gs_lo[L - 1]).view(p_g, 4, 256)[:n]
+            o_rows = torch.cat([xc_bar[:, None, :], jbar.permute(0, 2, 1)], 1)   # [n,4,3]
+            gw[0][L - 1] = o_rows.reshape(-1, 3).t() @ H8.reshape(-1, 256)
+            gb[0][L - 1] = xc_bar.sum(0)
+
+        grads: List[torch.Tensor] = []
+        for net in nets:
+            grads += gw[net] + gb[net]
+        return (None, None, None, None, *grads)
+
+
+def effective_weights(model) -> List[torch.Tensor]:
+    """[W_0..W_{L-1}, b_0..b_{L-1}] per network, differentiable w.r.t. weight_g / weight_v / bias."""
+    out = []
+    nets = ([model.deform_network] if model.use_deform else []) + [model.sdf_network, model.color_network]
+    for net in nets:
+        out += [l.effective_weight() for l in net.net]
+        out += [l.bias for l in net.net]
+    return out
+
+
+def composite(sdf, g_o, rgb, rays_d, pts, z_vals, sample_dist, inv_s, cos_ratio):
+    """NeuS alpha compositing of render_core (endosurf.py:168-203) in differentiable PyTorch (training path only;
+    inference uses the CUDA composite kernel).  sdf [R,M], g_o [R,M,3], rgb [R,M,3]."""
+    R, M = z_vals.shape
+    dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full((R, 1), sample_dist, device=z_vals.device)], -1)
+    mid_z = z_vals + dists * 0.5
+    true_cos = (rays_d[:, None, :] * g_o).sum(-1)
+    iter_cos = -(torch.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_ratio) + torch.relu(-true_cos) * cos_ratio)
+    prev_cdf = torch.sigmoid((sdf - iter_cos * dists * 0.5) * inv_s)
+    next_cdf = torch.sigmoid((sdf + iter_cos * dists * 0.5) * inv_s)
+    alpha = ((prev_cdf - next_cdf + 1e-6) / (prev_cdf + 1e-6)).clip(0.0, 1.0)
+    ones = torch.ones(R, 1, device=z_vals.device)
+    weights = alpha * torch.cumprod(torch.cat([ones, 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    relax = (torch.linalg.norm(pts, dim=-1) < 1.2).to(sdf.dtype).detach()
+    g_err = (torch.linalg.norm(g_o, dim=-1) - 1.0) ** 2
+    g_err = (relax * g_err).sum() / (relax.sum() + 1e-6)
+    return {
+        "color_map": (rgb * weights[:, :, None]).sum(1),
+        "depth_map": (weights * mid_z).sum(-1, keepdim=True),
+        "gradients_o": g_o,
+        "gradient_o_error": g_err,
+        "weights": weights,
+        "cdf": prev_cdf,
+    }

@@ -68,6 +68,28 @@ int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div,
                      int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac, float* sdf, float* g_c,
                      float* feat, float* rgb, void* stream);
 
+/* ---- differentiable (training) path -------------------------------------------------------------------------------
+ * The reference differentiates EndoSurfNet.forward with torch.autograd (create_graph=True at endosurf.py:594-658 so
+ * that the eikonal / colour losses can back-propagate through the normals).  Here the forward keeps, per MMA layer,
+ * the layer input of every row (primal + 3 tangent rows per point) as fp16 hi/lo planes ("stash"), and the reverse
+ * pass runs the same fused tcgen05 chains on transposed weights, writing the adjoint of every forward
+ * pre-activation ("zbar") so that weight gradients are plain [256 x rows] x [rows x 256] GEMMs.
+ *   es_train_layout: out6 = {geometry stash rows, geometry stash slots, colour stash rows, colour stash slots,
+ *                            zbar slots per reverse chain, geometry slot offset of the sdf layers}.
+ *   Planes are uint16 (fp16 bits) [slots][rows][256]; geometry rows are ordered point-major: row = 4*point + stream
+ *   (stream 0 = primal, 1..3 = d/dx, d/dy, d/dz), colour rows = point.                                             */
+int es_train_layout(const es_ctx* ctx, int64_t n, int64_t* out6);
+int es_point_forward_train(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
+                           const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
+                           float* sdf, float* g_c, float* feat, float* rgb, uint16_t* geom_stash_hi,
+                           uint16_t* geom_stash_lo, uint16_t* color_stash_hi, uint16_t* color_stash_lo, void* stream);
+/* Reverse chain of one network (net = ES_NET_*).  adj: [logical rows][4] = adjoint of the row's 3-wide output
+ * (deform: d/dDelta on primal rows, d/d(dDelta/dx_j) on tangent rows; colour: d/d(pre-sigmoid rgb)) in xyz and of the
+ * sdf-row output in w (sdf chain: d/dsdf on primal rows, d/dg_c[j] on tangent rows).  adj_feat: d/dfeat [n,256]
+ * (sdf chain).  zbar planes: [zbar slots][rows][256], slot m = adjoint of forward layer m's pre-activation. */
+int es_point_backward(es_ctx* ctx, int net, int64_t n, const uint16_t* stash_hi, const uint16_t* stash_lo,
+                      const float* adj, const float* adj_feat, uint16_t* zbar_hi, uint16_t* zbar_lo, void* stream);
+
 /* EndoSurfRenderer.up_sample (endosurf.py:221-266) incl. sample_pdf(det=True) (utils.py:160-191).
  * rays [R,9]; z, sdf [R,n]; u_vals [n_imp] = linspace(.5/n_imp, 1-.5/n_imp); new_z [R,n_imp]. */
 int es_up_sample(es_ctx* ctx, const float* rays, int64_t n_rays, const float* z, const float* sdf, int32_t n,

@@ -229,10 +229,3 @@ def test_edge_cases(cfg, ckpt):
     for k in ["color_map", "depth_map"]:
         assert torch.isfinite(o[k]).all()
         assert_close(k, o[k], ref[k], 5e-4)
-
-
-def test_training_path_is_loud(cfg, ckpt):
-    r = _renderer(cfg, ckpt, 32, 32)
-    r.train()
-    with pytest.raises(NotImplementedError):
-        r.render_rays(torch.zeros(4, 9, device="cuda"), iter_step=0)
