@@ -68,6 +68,17 @@ def make_rays(n_rays, frame, hw=512, n_frames=60, seed=0):
     return torch.cat([o, d, torch.zeros(n_rays, 2), torch.full((n_rays, 1), frame / (n_frames - 1))], -1).contiguous()
 
 
+def make_targets(n_rays, frame, seed=0):
+    g = torch.Generator().manual_seed(seed + 31 * frame + 5)
+    return torch.rand(n_rays, 3, generator=g), 0.5 + 0.5 * torch.rand(n_rays, 1, generator=g)
+
+
+def train_loss(o, color_gt, depth_gt):
+    """L1 colour + L1 depth + 0.1 eikonal: the render_rays part of the reference loss (trainer_endosurf.py:132-162)."""
+    return (o["color_map"] - color_gt).abs().mean() + (o["depth_map"] - depth_gt).abs().mean() + \
+        0.1 * o["gradient_o_error"]
+
+
 def seeded_state(renderer_module):
     """Random-init weights of the reference architecture: geometric SDF init + seeded noise (a deforming surface)."""
     g = torch.Generator().manual_seed(1234)
@@ -122,7 +133,7 @@ def measured_peak_tflops():
     return 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
 
 
-def oracle_cpu_rays_per_s(n_rays, repeats, threads):
+def oracle_cpu_rays_per_s(n_rays, repeats, threads, mode="train"):
     """Reference algorithm (oracle port; the reference is pure Python/PyTorch and cannot travel) on the host CPU."""
     from oracle import endosurf_oracle as orc  # checker / baseline only
     from endosurf_b200 import EndoSurfNet
@@ -130,15 +141,27 @@ def oracle_cpu_rays_per_s(n_rays, repeats, threads):
     torch.manual_seed(0)
     model = EndoSurfNet(NET_CFG)
     seeded_state(model)
-    ck = {k: {kk: vv.detach() for kk, vv in sd.items()} for k, sd in model.save_checkpoint().items()}
+    train = mode == "train"
+    ck = {k: {kk: vv.detach().clone().requires_grad_(train) for kk, vv in sd.items()}
+          for k, sd in model.save_checkpoint().items()}
     net = orc.OracleNet(ck, NET_CFG)
     rc = copy.deepcopy(RENDER_CFG)
+    params = [p for sd in ck.values() for p in sd.values()]
+    opt = torch.optim.Adam(params, lr=5e-4) if train else None
     times = []
     for i in range(repeats + 1):
         rays = make_rays(n_rays, frame=i)
+        cgt, dgt = make_targets(n_rays, frame=i)
         t0 = time.perf_counter()
-        with torch.no_grad():
-            orc.render_rays(net, rc, rays, iter_step=ITER_STEP)
+        if train:
+            opt.zero_grad()
+            o = orc.render_rays(net, rc, rays, iter_step=ITER_STEP)
+            loss = train_loss(o, cgt, dgt)
+            loss.backward()
+            opt.step()
+        else:
+            with torch.no_grad():
+                orc.render_rays(net, rc, rays, iter_step=ITER_STEP)
         times.append(time.perf_counter() - t0)
     t = float(np.median(times[1:])) if repeats > 0 else times[0]
     return n_rays / t, t
@@ -151,40 +174,65 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     n = args.ref_rays
     from oracle import endosurf_oracle as orc  # noqa
-    v, _ = oracle_cpu_rays_per_s(n, 0, threads)  # warm the allocator / thread pool
+    v, _ = oracle_cpu_rays_per_s(n, 0, threads, args.mode)  # warm the allocator / thread pool
     times = []
     for _ in range(max(args.warmup - 1, 0)):
-        oracle_cpu_rays_per_s(n, 0, threads)
+        oracle_cpu_rays_per_s(n, 0, threads, args.mode)
     for _ in range(args.steps):
-        _, t = oracle_cpu_rays_per_s(n, 0, threads)
+        _, t = oracle_cpu_rays_per_s(n, 0, threads, args.mode)
         times.append(t)
     ms = 1e3 * float(np.mean(times))
     val = n / (ms * 1e-3)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRICS[args.mode], "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.rays),
+        "config": workload_config(args.rays, mode=args.mode),
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} rays x (64+64 samples, 4 up-sampling steps) per step, forward, torch "
+                         "sample": f"{n} rays x (64+64 samples, 4 up-sampling steps) per step, {args.mode}, torch "
                                    f"{torch.__version__} CPU fp32, {threads} threads"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-METRIC = "render_rays forward rays/sec (512x512 frames, 64+64 samples)"
+METRICS = {"train": "training rays/sec (512x512 frames, 64+64 samples)",
+           "forward": "render_rays forward rays/sec (512x512 frames, 64+64 samples)"}
+METRIC = METRICS["train"]
 
 
-def workload_config(n_rays, note=None):
-    c = {"workload": f"render_rays forward, {n_rays}-ray batch of one 512x512 frame, 64 coarse + 64 fine samples, "
+def train_flops_per_ray(ns, ni, steps):
+    """SURVEY 8d convention: up-sampling x1 + render_core x3 (forward + ~2x backward)."""
+    m = ns + ni
+    u = ns + (steps - 1) * ni // steps if ni > 0 else 0
+    return 2.0 * (u * (D_MAC + S_MAC) + 3 * m * (4 * D_MAC + 2 * S_MAC + C_MAC))
+
+
+def workload_config(n_rays, note=None, mode="train"):
+    what = ("training step (render_rays forward + L1 colour/depth + eikonal loss, backward, Adam)" if mode == "train"
+            else "render_rays forward")
+    c = {"workload": f"{what}, {n_rays}-ray batch of one 512x512 frame, 64 coarse + 64 fine samples, "
                      "4 up-sampling steps, deform+sdf+colour 9x256 MLPs, fp32-parity (fp16 hi/lo x3) tensor-core mode",
          "rays_per_step_per_gpu": n_rays, "n_samples": 64, "n_importance": 64, "up_sample_steps": 4,
-         "parallelism": "rays sharded per rank, no data-path collective (forward)",
+         "parallelism": ("rays sharded per rank; one NCCL all-reduce of the flat 1.65 M-float gradient bucket per step"
+                         if mode == "train" else "rays sharded per rank, no data-path collective (forward)"),
          "l2_policy": "per-step working set (>= 1 GiB of per-point scratch) exceeds the 126 MB L2; ray batches rotate"}
     if note:
         c["note"] = note
     return c
+
+
+def allreduce_gradients(params, world):
+    """Data parallelism over ray batches: ONE all-reduce of the flat gradient bucket per step."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
 
 
 def run_ours(args):
@@ -198,56 +246,79 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from endosurf_b200 import EndoSurfRenderer
 
+    train = args.mode == "train"
     torch.manual_seed(0)
     r = EndoSurfRenderer(copy.deepcopy(RENDER_CFG), NET_CFG, device=f"cuda:{local}")
     seeded_state(r.model)
-    r.eval()
+    r.train(train)
+    params = [p for v in r.get_train_params().values() for p in v]
+    opt = torch.optim.Adam(params, lr=5e-4) if train else None
     R, K, W = args.rays, args.steps, args.warmup
     n_batches = min(K + W, 16)
-    host = [make_rays(R, frame=(rank * 17 + i) % 60, seed=rank).pin_memory() for i in range(n_batches)]
+    frames = [(rank * 17 + i) % 60 for i in range(n_batches)]
+    host = [make_rays(R, frame=f, seed=rank).pin_memory() for f in frames]
+    host_t = [tuple(x.pin_memory() for x in make_targets(R, frame=f, seed=rank)) for f in frames]
     devb = [h.to(dev) for h in host]
+    devt = [(c.to(dev), d.to(dev)) for c, d in host_t]
     out_c = torch.empty(R, 3).pin_memory()
     out_d = torch.empty(R, 1).pin_memory()
+    out_l = torch.empty(()).pin_memory()
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.no_grad():
-        for i in range(W):
-            r.render_rays(devb[i % n_batches], iter_step=ITER_STEP)
-        r.sync_check()
-        # ---------------- device-resident timing (value) + per-kernel roofline
-        r.profile(True)
-        launches0 = r.launch_count()
-        clocks = ClockSampler(local)
-        sync_all()
-        if rank == 0:
-            clocks.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(K):
-            r.render_rays(devb[(W + i) % n_batches], iter_step=ITER_STEP)
-        e1.record()
-        sync_all()
-        ms_total = e0.elapsed_time(e1)
-        clk = clocks.stop() if rank == 0 else None
-        launches = r.launch_count() - launches0
-        prof = r.profile_read()
-        r.profile(False)
-        # ---------------- end to end: pinned host rays in, colour + depth back to the host, every step
-        sync_all()
-        t0 = time.perf_counter()
-        for i in range(K):
-            rays = host[(W + i) % n_batches].to(dev, non_blocking=True)
-            o = r.render_rays(rays, iter_step=ITER_STEP)
-            out_c.copy_(o["color_map"], non_blocking=True)
-            out_d.copy_(o["depth_map"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        sync_all()
-        e2e_s = time.perf_counter() - t0
-        r.sync_check()
+    def step(rays, cgt, dgt):
+        if train:
+            opt.zero_grad(set_to_none=True)
+            o = r(rays, iter_step=ITER_STEP)
+            loss = train_loss(o, cgt, dgt)
+            loss.backward()
+            if world > 1:
+                allreduce_gradients(params, world)
+            opt.step()
+            return o, loss
+        with torch.no_grad():
+            return r.render_rays(rays, iter_step=ITER_STEP), None
+
+    for i in range(W):
+        step(devb[i % n_batches], *devt[i % n_batches])
+    r.sync_check()
+    # ---------------- device-resident timing (value) + per-kernel roofline
+    r.profile(True)
+    launches0 = r.launch_count()
+    clocks = ClockSampler(local)
+    sync_all()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(devb[(W + i) % n_batches], *devt[(W + i) % n_batches])
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = r.launch_count() - launches0
+    prof = r.profile_read()
+    r.profile(False)
+    # ---------------- end to end: pinned host rays (+ targets) in, colour + depth (+ loss) back to the host, every step
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(K):
+        j = (W + i) % n_batches
+        rays = host[j].to(dev, non_blocking=True)
+        cgt, dgt = (x.to(dev, non_blocking=True) for x in host_t[j])
+        o, loss = step(rays, cgt, dgt)
+        out_c.copy_(o["color_map"].detach(), non_blocking=True)
+        out_d.copy_(o["depth_map"].detach(), non_blocking=True)
+        if loss is not None:
+            out_l.copy_(loss.detach(), non_blocking=True)  # the reference reads loss.item() every step
+        torch.cuda.current_stream().synchronize()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    r.sync_check()
 
     t = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
@@ -263,17 +334,21 @@ def run_ours(args):
         alg_flops_launch = pts_per_launch * 2.0 * (4 * D_MAC + 2 * S_MAC)
         ms_launch = g["ms"] / max(g["launches"], 1)
         achieved = alg_flops_launch / (ms_launch * 1e-3) / 1e12 if ms_launch > 0 else 0.0
-        kern_ms = {k: v["ms"] / K for k, v in prof.items()}
+        kern_ms = {k: round(v["ms"] / K, 4) for k, v in prof.items()}
+        fpr = train_flops_per_ray(64, 64, 4) if train else flops_per_ray(64, 64, 4)
+        h2d = R * 9 * 4 + (R * 4 * 4 if train else 0)
+        d2h = R * 4 * 4 + (4 if train else 0)
         line = {
-            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRICS[args.mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (fp16 hi/lo x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
-            "config": workload_config(R),
-            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": R * 9 * 4, "d2h_bytes_per_step": R * 4 * 4,
+            "config": workload_config(R, mode=args.mode),
+            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "mlp_chain_kernel<CHAIN_SDF,TANGENT> (geometry chain)",
+            "roofline": {"bound": "tensor", "kernel": "mlp_chain_kernel<CHAIN_SDF,TANGENT> (forward geometry chain: "
+                                                      "deform+sdf MLPs with 3 forward-mode tangent rows per point)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
                          "algorithmic_flops_per_launch": alg_flops_launch, "points_per_launch": pts_per_launch,
@@ -282,14 +357,14 @@ def run_ours(args):
                                  "product (hi/lo split) and 4D+4S+feat (forward-mode normals), i.e. ~3.6x the "
                                  "algorithmic MMA work, so frac <= ~0.28 by construction",
                          "kernel_ms_per_step": kern_ms,
-                         "step_algorithmic_tflops": value / world * flops_per_ray(64, 64, 4) / 1e12},
+                         "step_algorithmic_tflops": value / world * fpr / 1e12},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, tt = oracle_cpu_rays_per_s(args.ref_rays, 1, threads)
+            v, tt = oracle_cpu_rays_per_s(args.ref_rays, 1, threads, args.mode)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                                    "sample": f"{args.ref_rays} rays of the same workload, forward, oracle port of "
-                                              f"the reference (PyTorch {torch.__version__} CPU fp32), {tt:.1f} s"}
+                                    "sample": f"{args.ref_rays} rays of the same workload ({args.mode}), oracle port "
+                                              f"of the reference (PyTorch {torch.__version__} CPU fp32), {tt:.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -302,8 +377,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=4096, help="rays per step per GPU (BASELINE configs[1])")
-    ap.add_argument("--ref-rays", type=int, default=128, help="bounded CPU sample per step for the reference arm")
+    ap.add_argument("--ref-rays", type=int, default=64, help="bounded CPU sample per step for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "forward"],
+                    help="train: BASELINE.json's metric (training rays/s); forward: inference render_rays")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -33,7 +33,7 @@ class EsRenderOut(C.Structure):
 
 
 class EsProfile(C.Structure):
-    _fields_ = [("ms", C.c_double * 3), ("launches", C.c_int64 * 3), ("points", C.c_int64 * 3)]
+    _fields_ = [("ms", C.c_double * 6), ("launches", C.c_int64 * 6), ("points", C.c_int64 * 6)]
 
 
 EXPORTS = {

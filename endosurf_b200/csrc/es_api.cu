@@ -521,7 +521,7 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
 }
 
 static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const ChainProg& prog, const ChainIO& io,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, bool bwd = false) {
   es_ctx::Timed t{kind, io.n_points, nullptr, nullptr};
   ChainIO io2 = io;
   io2.trace = ctx->trace_dev;
@@ -534,7 +534,7 @@ static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const Cha
     CU(cudaEventCreate(&t.e1));
     CU(cudaEventRecord(t.e0, stream));
   }
-  CU(launch_mlp_chain(chain, tangent, ctx->cfg.use_deform != 0, prog, io2, ctx->n_sms, stream));
+  CU(launch_mlp_chain(chain, tangent, ctx->cfg.use_deform != 0, prog, io2, ctx->n_sms, stream, bwd));
   ++ctx->launches;
   if (ctx->profiling) {
     CU(cudaEventRecord(t.e1, stream));
@@ -690,10 +690,8 @@ int es_point_backward(es_ctx* ctx, int net, int64_t n, const uint16_t* stash_hi,
   io.adj_feat = adj_feat;
   io.t_div = 1;
   io.dir_div = 1;
-  CU(launch_mlp_chain(tangent ? CHAIN_SDF : CHAIN_COLOR, tangent, true, ctx->prog_rev[net], io, ctx->n_sms,
-                      static_cast<cudaStream_t>(stream), true));
-  ++ctx->launches;
-  return 0;
+  return timed_chain(ctx, 3 + net, tangent ? CHAIN_SDF : CHAIN_COLOR, tangent, ctx->prog_rev[net], io,
+                     static_cast<cudaStream_t>(stream), true);
 }
 
 int es_up_sample(es_ctx* ctx, const float* rays, int64_t n_rays, const float* z, const float* sdf, int32_t n,

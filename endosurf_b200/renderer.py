@@ -360,7 +360,8 @@ class EndoSurfRenderer(nn.Module):
         lib, ctx = _lib.load(), self._context()
         p = _lib.EsProfile()
         _lib.check(ctx, lib.es_profile_read(ctx, C.byref(p), self._stream()), "es_profile_read")
-        names = ["geometry_chain", "color_chain", "sdf_query_chain"]
+        names = ["geometry_chain", "color_chain", "sdf_query_chain", "rev_deform_chain", "rev_sdf_chain",
+                 "rev_color_chain"]
         return {n: {"ms": p.ms[i], "launches": int(p.launches[i]), "points": int(p.points[i])}
                 for i, n in enumerate(names)}
 

@@ -55,6 +55,29 @@ def planes_f32(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
     return hi.view(torch.float16).float() + lo.view(torch.float16).float()
 
 
+_MM_OUT_DTYPE_OK = None
+
+
+def tn_planes(z_hi, z_lo, h_hi, h_lo, min_rows_fast=65536) -> torch.Tensor:
+    """zbar^T @ stash for two [rows, 256] operands held as fp16 hi/lo planes -> [256, 256] fp32.
+    Large row counts use three fp16 tensor-core library GEMMs with fp32 output (hi*hi + hi*lo + lo*hi, the same split
+    as the fused kernels); small ones (tests) the exact fp32 product."""
+    global _MM_OUT_DTYPE_OK
+    zh, zl = z_hi.view(torch.float16), z_lo.view(torch.float16)
+    hh, hl = h_hi.view(torch.float16), h_lo.view(torch.float16)
+    if zh.shape[0] >= min_rows_fast and _MM_OUT_DTYPE_OK is not False:
+        try:
+            zt_h, zt_l = zh.t(), zl.t()
+            out = torch.mm(zt_h, hh, out_dtype=torch.float32)
+            out += torch.mm(zt_h, hl, out_dtype=torch.float32)
+            out += torch.mm(zt_l, hh, out_dtype=torch.float32)
+            _MM_OUT_DTYPE_OK = True
+            return out
+        except (TypeError, RuntimeError):
+            _MM_OUT_DTYPE_OK = False
+    return (zh.float() + zl.float()).t() @ (hh.float() + hl.float())
+
+
 def _pow2_scale(*tensors) -> torch.Tensor:
     """Power-of-two loss scale so that the largest adjoint entering a reverse chain is ~16 (fp16 hi/lo planes keep
     22 bits relative to that; no host sync)."""
@@ -171,8 +194,7 @@ class PointFieldFn(torch.autograd.Function):
         gb[2][0] = Z0.sum(0)
         for m in range(1, L - 1):
             Zm = zbar(zc_hi, zc_lo, m, s_c)
-            Hm = planes_f32(cs_hi[m], cs_lo[m])
-            g = Zm.t() @ Hm
+            g = tn_planes(zc_hi[m], zc_lo[m], cs_hi[m], cs_lo[m]) / s_c
             if m == skip:
                 inp_bar = inp_bar + Zm[:n] @ (Wc[m][:, 256:] / SQRT2)
                 g = torch.cat([g, Zm[:n].t() @ inp_c], 1) / SQRT2
@@ -215,8 +237,7 @@ class PointFieldFn(torch.autograd.Function):
             gb[1][0] = Z0[:, 0].sum(0)
             for m in range(1, L - 1):
                 Zm = zbar(zs_hi, zs_lo, m, s_s)
-                Hm = planes_f32(gs_hi[sdf_off + m], gs_lo[sdf_off + m])
-                g = Zm.t() @ Hm
+                g = tn_planes(zs_hi[m], zs_lo[m], gs_hi[sdf_off + m], gs_lo[sdf_off + m]) / s_s
                 Zp = Zm.view(p_g, 4, 256)[:n]
                 if m == skip:
                     E = E + Zp @ (Ws[m][:, 256:] / SQRT2)
@@ -250,8 +271,7 @@ class PointFieldFn(torch.autograd.Function):
             gb[0][0] = Z0[:, 0].sum(0)
             for m in range(1, L - 1):
                 Zm = zbar(zd_hi, zd_lo, m, s_d)
-                Hm = planes_f32(gs_hi[m], gs_lo[m])
-                g = (Zm.t() @ Hm)[:out_dims[m]]
+                g = (tn_planes(zd_hi[m], zd_lo[m], gs_hi[m], gs_lo[m]) / s_d)[:out_dims[m]]
                 Zp = Zm.view(p_g, 4, 256)[:n]
                 if m == skip:
                     hprev = out_dims[m - 1]

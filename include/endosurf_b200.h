@@ -130,11 +130,11 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
 /* Per-kernel device timing for bench.py's roofline: when enabled every fused MLP-chain launch is bracketed with
  * CUDA events on the launching stream.  es_profile_read synchronises the stream, returns the accumulated durations
  * since the last read and resets them.  kind: 0 = geometry chain (deform+sdf with tangent rows and feature layer),
- * 1 = colour chain, 2 = sdf query chain. */
+ * 1 = colour chain, 2 = sdf query chain, 3/4/5 = reverse (training) chain of the deform / sdf / colour network. */
 typedef struct es_profile {
-  double ms[3];
-  int64_t launches[3];
-  int64_t points[3];
+  double ms[6];
+  int64_t launches[6];
+  int64_t points[6];
 } es_profile;
 int es_profile_enable(es_ctx* ctx, int32_t on);
 int es_profile_read(es_ctx* ctx, es_profile* out, void* stream);

@@ -26,7 +26,10 @@ print("loss", loss.item(), ref_loss.item())
 loss.backward(); r.sync_check()
 for name, p in r.model.named_parameters():
     nn, rest = name.split(".", 1)
-    gr = ck[nn][rest].grad; gm = p.grad.cpu()
+    gr = ck[nn][rest].grad
+    if p.grad is None or gr is None:
+        print(name, "no grad"); continue
+    gm = p.grad.cpu()
     e = (gm - gr).norm().item() / max(gr.norm().item(), 1e-12)
     flag = "  <<<<" if e > 2e-3 else ""
     print(f"{name:42s} ref {gr.norm().item():10.3e} mine {gm.norm().item():10.3e} rel err {e:9.2e}{flag}")
