@@ -274,7 +274,7 @@ class EndoSurfRenderer(nn.Module):
         return self._consts[key]
 
     # ------------------------------------------------------------------ differentiable (training) path
-    train_ray_chunk = 1024  # rays per autograd.Function call: bounds the activation stash (about 10 GiB per chunk)
+    train_ray_chunk = 2048  # rays per autograd.Function call: bounds the activation stash (about 21 GiB per chunk)
 
     def point_field(self, x, d, t):
         """Differentiable EndoSurfNet.forward + gradient queries on explicit points:

@@ -56,26 +56,48 @@ def planes_f32(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
 
 
 _MM_OUT_DTYPE_OK = None
+FAST_MIN_ROWS = 32768  # below this the exact fp32 product is cheap (tests); above, fp16 tensor-core library GEMMs
 
 
-def tn_planes(z_hi, z_lo, h_hi, h_lo, min_rows_fast=65536) -> torch.Tensor:
-    """zbar^T @ stash for two [rows, 256] operands held as fp16 hi/lo planes -> [256, 256] fp32.
-    Large row counts use three fp16 tensor-core library GEMMs with fp32 output (hi*hi + hi*lo + lo*hi, the same split
-    as the fused kernels); small ones (tests) the exact fp32 product."""
+def _mm16(a16: torch.Tensor, b16: torch.Tensor) -> torch.Tensor:
+    return torch.mm(a16, b16, out_dtype=torch.float32)
+
+
+def split16(x: torch.Tensor):
+    """fp32 -> (hi, lo) fp16 with x ~= hi + lo (22 bits), the same split the kernels use."""
+    hi = x.to(torch.float16)
+    return hi, (x - hi.float()).to(torch.float16)
+
+
+def tn_planes(a_hi, a_lo, b_hi, b_lo) -> torch.Tensor:
+    """A^T @ B for A [rows, a], B [rows, b] held as fp16 hi/lo planes -> [a, b] fp32.
+    Large row counts: three fp16 tensor-core library GEMMs with fp32 output (hi*hi + hi*lo + lo*hi, the split the
+    fused kernels use; these are plain GEMMs, cuBLAS picks a split-K kernel); small ones: the exact fp32 product."""
     global _MM_OUT_DTYPE_OK
-    zh, zl = z_hi.view(torch.float16), z_lo.view(torch.float16)
-    hh, hl = h_hi.view(torch.float16), h_lo.view(torch.float16)
-    if zh.shape[0] >= min_rows_fast and _MM_OUT_DTYPE_OK is not False:
+    ah, al = a_hi.view(torch.float16), a_lo.view(torch.float16)
+    bh, bl = b_hi.view(torch.float16), b_lo.view(torch.float16)
+    if ah.shape[0] >= FAST_MIN_ROWS and _MM_OUT_DTYPE_OK is not False:
         try:
-            zt_h, zt_l = zh.t(), zl.t()
-            out = torch.mm(zt_h, hh, out_dtype=torch.float32)
-            out += torch.mm(zt_h, hl, out_dtype=torch.float32)
-            out += torch.mm(zt_l, hh, out_dtype=torch.float32)
+            at_h, at_l = ah.t(), al.t()
+            out = _mm16(at_h, bh)
+            out += _mm16(at_h, bl)
+            out += _mm16(at_l, bh)
             _MM_OUT_DTYPE_OK = True
             return out
         except (TypeError, RuntimeError):
             _MM_OUT_DTYPE_OK = False
-    return (zh.float() + zl.float()).t() @ (hh.float() + hl.float())
+    return (ah.float() + al.float()).t() @ (bh.float() + bl.float())
+
+
+def rowsum_planes(hi, lo, sel16: torch.Tensor) -> torch.Tensor:
+    """sum over the rows selected by the 0/1 fp16 row vector sel16 [1, rows] of a hi/lo plane pair -> [cols] fp32."""
+    h, l = hi.view(torch.float16), lo.view(torch.float16)
+    if h.shape[0] >= FAST_MIN_ROWS and _MM_OUT_DTYPE_OK is not False:
+        try:
+            return (_mm16(sel16, h) + _mm16(sel16, l))[0]
+        except (TypeError, RuntimeError):
+            pass
+    return (sel16.float() @ (h.float() + l.float()))[0]
 
 
 def _pow2_scale(*tensors) -> torch.Tensor:
@@ -169,6 +191,12 @@ class PointFieldFn(torch.autograd.Function):
         gw = {net: [None] * L for net in nets}
         gb = {net: [None] * L for net in nets}
         p_g = g_rows // 4  # padded point count of the geometry chains
+        f16 = torch.float16
+        # 0/1 row selectors for bias gradients (tangent rows carry no bias)
+        ones_c = torch.ones(1, c_rows, dtype=f16, device=dev)
+        prim_g = torch.zeros(p_g, 4, dtype=f16, device=dev)
+        prim_g[:, 0] = 1
+        prim_g = prim_g.reshape(1, g_rows)
 
         def run_reverse(net, adj, adj_feat, stash_hi, stash_lo, rows):
             zb_hi = torch.empty(z_slots, rows, 256, dtype=torch.int16, device=dev)
@@ -178,30 +206,41 @@ class PointFieldFn(torch.autograd.Function):
             _lib.check(ectx, rc, "es_point_backward")
             return zb_hi, zb_lo
 
+        def padded_planes(v, rows):
+            """[n, k] fp32 (per point) or [n, 4, k] (per row) -> hi/lo planes zero-padded to the stash row count."""
+            v = v.reshape(-1, v.shape[-1])
+            buf = torch.zeros(rows, v.shape[1], device=dev)
+            buf[:v.shape[0]] = v
+            return split16(buf)
+
         # ============================================================== colour network
         d_c_u = torch.bmm(jac, d.unsqueeze(-1)).squeeze(-1)
         d_c = d_c_u / (torch.linalg.norm(d_c_u, dim=-1, keepdim=True) + 1e-10)
         inp_c = torch.cat([freq_enc(x_c, cfg.multires_color_pos), g_c, freq_enc(d_c, cfg.multires_color_dir), feat], -1)
+        inp_hi, inp_lo = padded_planes(inp_c, c_rows)
         o_c = rgb_bar * rgb * (1.0 - rgb)                     # through the output sigmoid (endosurf.py:841)
         s_c = _pow2_scale(o_c)
         adj_c = torch.cat([o_c * s_c, torch.zeros(n, 1, device=dev)], -1).contiguous()
         zc_hi, zc_lo = run_reverse(2, adj_c, None, cs_hi, cs_lo, c_rows)
         Wc = ws[2]
-        zbar = lambda hi, lo, m, s: planes_f32(hi[m], lo[m]) / s
-        Z0 = zbar(zc_hi, zc_lo, 0, s_c)
-        inp_bar = Z0[:n] @ Wc[0]
-        gw[2][0] = Z0[:n].t() @ inp_c
-        gb[2][0] = Z0.sum(0)
-        for m in range(1, L - 1):
-            Zm = zbar(zc_hi, zc_lo, m, s_c)
-            g = tn_planes(zc_hi[m], zc_lo[m], cs_hi[m], cs_lo[m]) / s_c
-            if m == skip:
-                inp_bar = inp_bar + Zm[:n] @ (Wc[m][:, 256:] / SQRT2)
-                g = torch.cat([g, Zm[:n].t() @ inp_c], 1) / SQRT2
-            gw[2][m] = g
-            gb[2][m] = Zm.sum(0)
-        H_out = planes_f32(cs_hi[L - 1], cs_lo[L - 1])[:n]
-        gw[2][L - 1] = o_c.t() @ H_out
+        inp_bar = None
+        for m in range(0, L - 1):
+            if m == 0 or m == skip:  # layers that read the network input: need zbar itself for the input adjoint
+                Zm = planes_f32(zc_hi[m], zc_lo[m])[:n]
+                w_in = Wc[0] if m == 0 else Wc[m][:, 256:] / SQRT2
+                inp_bar = Zm @ w_in if inp_bar is None else inp_bar + Zm @ w_in
+            g_in = tn_planes(zc_hi[m], zc_lo[m], inp_hi, inp_lo) if (m == 0 or m == skip) else None
+            if m == 0:
+                g = g_in
+            else:
+                g = tn_planes(zc_hi[m], zc_lo[m], cs_hi[m], cs_lo[m])
+                if m == skip:
+                    g = torch.cat([g, g_in], 1) / SQRT2
+            gw[2][m] = g / s_c
+            gb[2][m] = rowsum_planes(zc_hi[m], zc_lo[m], ones_c) / s_c
+        inp_bar = inp_bar / s_c
+        oc_hi, oc_lo = padded_planes(o_c, c_rows)
+        gw[2][L - 1] = tn_planes(oc_hi, oc_lo, cs_hi[L - 1], cs_lo[L - 1])
         gb[2][L - 1] = o_c.sum(0)
         nx = 3 * (1 + 2 * cfg.multires_color_pos)
         nd = 3 * (1 + 2 * cfg.multires_color_dir)
@@ -216,6 +255,7 @@ class PointFieldFn(torch.autograd.Function):
             obj = (freq_enc(xc_r, cfg.multires_color_pos) * ex_bar).sum() + \
                 (freq_enc(dcr, cfg.multires_color_dir) * ed_bar).sum()
             xc_bar, jbar_color = torch.autograd.grad(obj, [xc_r, j_r])
+        del zc_hi, zc_lo, inp_hi, inp_lo
 
         # ============================================================== sdf network
         gc_tot = gc_bar + gc_col_bar
@@ -231,25 +271,33 @@ class PointFieldFn(torch.autograd.Function):
             e0 = freq_enc(xc_r, cfg.multires_sdf_pos)                     # [n, 39]
             et = freq_enc_tangent(xc_r, cfg.multires_sdf_pos)             # [n, 3, 39]
             a0 = torch.cat([e0[:, None, :], et], 1)                       # rows of the first sdf layer [n,4,39]
-            Z0 = zbar(zs_hi, zs_lo, 0, s_s).view(p_g, 4, 256)[:n]
-            E = Z0 @ Ws[0]                                                # adjoint of those rows [n,4,39]
-            gw[1][0] = Z0.reshape(-1, 256).t() @ a0.detach().reshape(-1, a0.shape[-1])
-            gb[1][0] = Z0[:, 0].sum(0)
-            for m in range(1, L - 1):
-                Zm = zbar(zs_hi, zs_lo, m, s_s)
-                g = tn_planes(zs_hi[m], zs_lo[m], gs_hi[sdf_off + m], gs_lo[sdf_off + m]) / s_s
-                Zp = Zm.view(p_g, 4, 256)[:n]
-                if m == skip:
-                    E = E + Zp @ (Ws[m][:, 256:] / SQRT2)
-                    g = torch.cat([g, Zp.reshape(-1, 256).t() @ a0.detach().reshape(-1, a0.shape[-1])], 1) / SQRT2
-                gw[1][m] = g
-                gb[1][m] = Zp[:, 0].sum(0)
-            xc_bar = xc_bar + torch.autograd.grad((a0 * E.detach()).sum(), xc_r)[0]
-        H8 = planes_f32(gs_hi[sdf_off + L - 1], gs_lo[sdf_off + L - 1]).view(p_g, 4, 256)[:n]
+            a0_hi, a0_lo = padded_planes(a0.detach(), g_rows)
+            E = None
+            for m in range(0, L - 1):
+                if m == 0 or m == skip:
+                    Zp = planes_f32(zs_hi[m], zs_lo[m]).view(p_g, 4, 256)[:n]
+                    w_in = Ws[0] if m == 0 else Ws[m][:, 256:] / SQRT2
+                    E = Zp @ w_in if E is None else E + Zp @ w_in            # adjoint of the input rows [n,4,39]
+                g_in = tn_planes(zs_hi[m], zs_lo[m], a0_hi, a0_lo) if (m == 0 or m == skip) else None
+                if m == 0:
+                    g = g_in
+                else:
+                    g = tn_planes(zs_hi[m], zs_lo[m], gs_hi[sdf_off + m], gs_lo[sdf_off + m])
+                    if m == skip:
+                        g = torch.cat([g, g_in], 1) / SQRT2
+                gw[1][m] = g / s_s
+                gb[1][m] = rowsum_planes(zs_hi[m], zs_lo[m], prim_g) / s_s
+            xc_bar = xc_bar + torch.autograd.grad((a0 * (E / s_s).detach()).sum(), xc_r)[0]
         r_rows = torch.cat([sdf_bar, gc_tot], 1)                          # [n,4]: adjoint of the sdf-row output
-        g_row0 = (r_rows.reshape(-1, 1) * H8.reshape(-1, 256)).sum(0, keepdim=True)
-        gw[1][L - 1] = torch.cat([g_row0, feat_bar.t() @ H8[:, 0]], 0)
+        rr_hi, rr_lo = padded_planes(r_rows.reshape(-1, 1), g_rows)
+        sl = sdf_off + L - 1
+        g_row0 = tn_planes(rr_hi, rr_lo, gs_hi[sl], gs_lo[sl])            # [1,256]
+        h8p_hi = gs_hi[sl].view(p_g, 4, 256)[:n, 0].contiguous()          # primal rows of the output layer's input
+        h8p_lo = gs_lo[sl].view(p_g, 4, 256)[:n, 0].contiguous()
+        fb_hi, fb_lo = split16(feat_bar)
+        gw[1][L - 1] = torch.cat([g_row0, tn_planes(fb_hi, fb_lo, h8p_hi, h8p_lo)], 0)
         gb[1][L - 1] = torch.cat([sdf_bar.sum(0), feat_bar.sum(0)], 0)
+        del zs_hi, zs_lo, a0_hi, a0_lo
 
         # ============================================================== deformation network
         if use_deform:
@@ -266,22 +314,20 @@ class PointFieldFn(torch.autograd.Function):
             tt = freq_enc(t.reshape(-1, 1), cfg.multires_deform_time)
             a0 = torch.cat([torch.cat([ex, tt], -1)[:, None, :],
                             torch.cat([etx, torch.zeros(n, 3, tt.shape[1], device=dev)], -1)], 1)  # [n,4,52]
-            Z0 = zbar(zd_hi, zd_lo, 0, s_d).view(p_g, 4, 256)[:n]
-            gw[0][0] = Z0.reshape(-1, 256).t() @ a0.reshape(-1, a0.shape[-1])
-            gb[0][0] = Z0[:, 0].sum(0)
-            for m in range(1, L - 1):
-                Zm = zbar(zd_hi, zd_lo, m, s_d)
-                g = (tn_planes(zd_hi[m], zd_lo[m], gs_hi[m], gs_lo[m]) / s_d)[:out_dims[m]]
-                Zp = Zm.view(p_g, 4, 256)[:n]
-                if m == skip:
-                    hprev = out_dims[m - 1]
-                    g = torch.cat([g[:, :hprev], (Zp.reshape(-1, 256).t() @ a0.reshape(-1, a0.shape[-1]))[:out_dims[m]]],
-                                  1) / SQRT2
-                gw[0][m] = g
-                gb[0][m] = Zp[:, 0].sum(0)[:out_dims[m]]
-            H8 = planes_f32(gs_hi[L - 1], gs_lo[L - 1]).view(p_g, 4, 256)[:n]
+            a0_hi, a0_lo = padded_planes(a0, g_rows)
+            for m in range(0, L - 1):
+                g_in = tn_planes(zd_hi[m], zd_lo[m], a0_hi, a0_lo) if (m == 0 or m == skip) else None
+                if m == 0:
+                    g = g_in
+                else:
+                    g = tn_planes(zd_hi[m], zd_lo[m], gs_hi[m], gs_lo[m])
+                    if m == skip:
+                        g = torch.cat([g[:, :out_dims[m - 1]], g_in], 1) / SQRT2
+                gw[0][m] = (g / s_d)[:out_dims[m]]
+                gb[0][m] = (rowsum_planes(zd_hi[m], zd_lo[m], prim_g) / s_d)[:out_dims[m]]
             o_rows = torch.cat([xc_bar[:, None, :], jbar.permute(0, 2, 1)], 1)   # [n,4,3]
-            gw[0][L - 1] = o_rows.reshape(-1, 3).t() @ H8.reshape(-1, 256)
+            or_hi, or_lo = padded_planes(o_rows, g_rows)
+            gw[0][L - 1] = tn_planes(or_hi, or_lo, gs_hi[L - 1], gs_lo[L - 1])
             gb[0][L - 1] = xc_bar.sum(0)
 
         grads: List[torch.Tensor] = []
