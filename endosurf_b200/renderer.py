@@ -267,6 +267,7 @@ class EndoSurfRenderer(nn.Module):
                 _lib.check(ctx, lib.es_load_network(ctx, net_id, wp, bp, self._stream()), "es_load_network")
         self._keepalive = keep  # folded tensors stay alive until the pack kernels have been enqueued and run
         self._packed_version = ver
+        self._loaded_epoch = None
 
     def _const(self, key, fn):
         if key not in self._consts:
@@ -276,11 +277,20 @@ class EndoSurfRenderer(nn.Module):
     # ------------------------------------------------------------------ differentiable (training) path
     train_ray_chunk = 2048  # rays per autograd.Function call: bounds the activation stash (about 21 GiB per chunk)
 
-    def point_field(self, x, d, t):
+    def point_field(self, x, d, t, wb=None):
         """Differentiable EndoSurfNet.forward + gradient queries on explicit points:
         (sdf [n,1], g_c [n,3], jac [n,3,3], rgb [n,3]); gradients flow to every network parameter."""
         from .training import PointFieldFn, effective_weights
-        return PointFieldFn.apply(self, x, d, t, *effective_weights(self.model))
+        if wb is None:
+            wb = self.effective_weights()
+        return PointFieldFn.apply(self, wb[0], x, d, t, *wb[1])
+
+    def effective_weights(self):
+        """(epoch, [W_l.., b_l..] per network): fold weight norm once per step; the epoch tags this parameter state
+        so that the CUDA context re-packs its fp16 operand units only when the weights actually changed."""
+        from .training import effective_weights
+        self._wb_epoch = getattr(self, "_wb_epoch", 0) + 1
+        return self._wb_epoch, effective_weights(self.model)
 
     def _sample_z(self, rays, iter_step, perturb_overwrite):
         """Coarse + hierarchical sampling only (no grad, CUDA): z_vals [R,M]."""
@@ -328,13 +338,14 @@ class EndoSurfRenderer(nn.Module):
         mid_z = z + dists * 0.5
         pts = rays_o[:, None, :] + d_z[:, None, :] * mid_z[..., None]
         sdf_l, go_l, rgb_l = [], [], []
+        wb = self.effective_weights()
         for r0 in range(0, R, self.train_ray_chunk):
             r1 = min(R, r0 + self.train_ray_chunk)
             n = (r1 - r0) * M
             x = pts[r0:r1].reshape(n, 3)
             dd = rays_d[r0:r1, None, :].expand(r1 - r0, M, 3).reshape(n, 3)
             tt = time[r0:r1, None].expand(r1 - r0, M).reshape(n, 1)
-            sdf, g_c, jac, rgb = self.point_field(x, dd, tt)
+            sdf, g_c, jac, rgb = self.point_field(x, dd, tt, wb)
             g_o = torch.einsum("nij,ni->nj", jac, g_c)  # = autograd normal in observed space
             sdf_l.append(sdf.reshape(r1 - r0, M))
             go_l.append(g_o.reshape(r1 - r0, M, 3))

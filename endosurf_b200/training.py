@@ -112,11 +112,24 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _upload(renderer, epoch, nets, ws, bs, L):
+    """Pack this call's effective weights into the context unless it already holds exactly them (same epoch)."""
+    if getattr(renderer, "_loaded_epoch", None) == epoch:
+        return
+    lib, ectx = _lib.load(), renderer._context()
+    for net in nets:
+        wp = (C.c_void_p * L)(*[w.data_ptr() for w in ws[net]])
+        bp = (C.c_void_p * L)(*[b.data_ptr() for b in bs[net]])
+        _lib.check(ectx, lib.es_load_network(ectx, net, wp, bp, renderer._stream()), "es_load_network")
+    renderer._loaded_epoch = epoch
+    renderer._packed_version = None  # the context now holds these weights, not necessarily the module's
+
+
 class PointFieldFn(torch.autograd.Function):
     """(x, d, t, effective weights...) -> (sdf [n,1], g_c [n,3], jac [n,3,3], rgb [n,3])."""
 
     @staticmethod
-    def forward(ctx, renderer, x, d, t, *wb):
+    def forward(ctx, renderer, epoch, x, d, t, *wb):
         lib, ectx = _lib.load(), renderer._context()
         stream = renderer._stream()
         n = x.shape[0]
@@ -130,10 +143,7 @@ class PointFieldFn(torch.autograd.Function):
             ws[net] = [w.detach().contiguous() for w in wb[k:k + L]]
             bs[net] = [b.detach().contiguous() for b in wb[k + L:k + 2 * L]]
             k += 2 * L
-            wp = (C.c_void_p * L)(*[w.data_ptr() for w in ws[net]])
-            bp = (C.c_void_p * L)(*[b.data_ptr() for b in bs[net]])
-            _lib.check(ectx, lib.es_load_network(ectx, net, wp, bp, stream), "es_load_network")
-        renderer._packed_version = None  # the context now holds these weights, not necessarily the module's
+        _upload(renderer, epoch, nets, ws, bs, L)
         lay = (C.c_int64 * 6)()
         _lib.check(ectx, lib.es_train_layout(ectx, n, lay), "es_train_layout")
         g_rows, g_slots, c_rows, c_slots, z_slots, sdf_off = [int(v) for v in lay]
@@ -158,6 +168,7 @@ class PointFieldFn(torch.autograd.Function):
         if not use_deform:
             jac = torch.eye(3, device=dev).expand(n, 3, 3).contiguous()
         ctx.renderer = renderer
+        ctx.epoch = epoch
         ctx.meta = (n, L, use_deform, nets, g_rows, g_slots, c_rows, c_slots, z_slots, sdf_off)
         ctx.ws, ctx.bs = ws, bs
         ctx.save_for_backward(x, d, t, x_c, jac, g_c, feat, rgb, gs_hi, gs_lo, cs_hi, cs_lo)
@@ -175,11 +186,7 @@ class PointFieldFn(torch.autograd.Function):
         cfg = renderer._cfg_struct
         skip = cfg.skip_layer
         # the context may have been re-packed by another forward since; make sure it holds THIS call's weights
-        for net in nets:
-            wp = (C.c_void_p * L)(*[w.data_ptr() for w in ws[net]])
-            bp = (C.c_void_p * L)(*[b.data_ptr() for b in bs[net]])
-            _lib.check(ectx, lib.es_load_network(ectx, net, wp, bp, stream), "es_load_network")
-        renderer._packed_version = None
+        _upload(renderer, ctx.epoch, nets, ws, bs, L)
 
         def zeros_like_or(tns, shape):
             return tns if tns is not None else torch.zeros(shape, device=dev)
@@ -209,8 +216,9 @@ class PointFieldFn(torch.autograd.Function):
         def padded_planes(v, rows):
             """[n, k] fp32 (per point) or [n, 4, k] (per row) -> hi/lo planes zero-padded to the stash row count."""
             v = v.reshape(-1, v.shape[-1])
-            buf = torch.zeros(rows, v.shape[1], device=dev)
-            buf[:v.shape[0]] = v
+            cols = (v.shape[1] + 15) // 16 * 16   # odd widths push cuBLAS onto legacy kernels
+            buf = torch.zeros(rows, cols, device=dev)
+            buf[:v.shape[0], :v.shape[1]] = v
             return split16(buf)
 
         # ============================================================== colour network
@@ -229,7 +237,7 @@ class PointFieldFn(torch.autograd.Function):
                 Zm = planes_f32(zc_hi[m], zc_lo[m])[:n]
                 w_in = Wc[0] if m == 0 else Wc[m][:, 256:] / SQRT2
                 inp_bar = Zm @ w_in if inp_bar is None else inp_bar + Zm @ w_in
-            g_in = tn_planes(zc_hi[m], zc_lo[m], inp_hi, inp_lo) if (m == 0 or m == skip) else None
+            g_in = tn_planes(zc_hi[m], zc_lo[m], inp_hi, inp_lo)[:, :inp_c.shape[1]] if (m == 0 or m == skip) else None
             if m == 0:
                 g = g_in
             else:
@@ -240,7 +248,7 @@ class PointFieldFn(torch.autograd.Function):
             gb[2][m] = rowsum_planes(zc_hi[m], zc_lo[m], ones_c) / s_c
         inp_bar = inp_bar / s_c
         oc_hi, oc_lo = padded_planes(o_c, c_rows)
-        gw[2][L - 1] = tn_planes(oc_hi, oc_lo, cs_hi[L - 1], cs_lo[L - 1])
+        gw[2][L - 1] = tn_planes(oc_hi, oc_lo, cs_hi[L - 1], cs_lo[L - 1])[:3]
         gb[2][L - 1] = o_c.sum(0)
         nx = 3 * (1 + 2 * cfg.multires_color_pos)
         nd = 3 * (1 + 2 * cfg.multires_color_dir)
@@ -278,7 +286,7 @@ class PointFieldFn(torch.autograd.Function):
                     Zp = planes_f32(zs_hi[m], zs_lo[m]).view(p_g, 4, 256)[:n]
                     w_in = Ws[0] if m == 0 else Ws[m][:, 256:] / SQRT2
                     E = Zp @ w_in if E is None else E + Zp @ w_in            # adjoint of the input rows [n,4,39]
-                g_in = tn_planes(zs_hi[m], zs_lo[m], a0_hi, a0_lo) if (m == 0 or m == skip) else None
+                g_in = tn_planes(zs_hi[m], zs_lo[m], a0_hi, a0_lo)[:, :a0.shape[-1]] if (m == 0 or m == skip) else None
                 if m == 0:
                     g = g_in
                 else:
@@ -291,7 +299,7 @@ class PointFieldFn(torch.autograd.Function):
         r_rows = torch.cat([sdf_bar, gc_tot], 1)                          # [n,4]: adjoint of the sdf-row output
         rr_hi, rr_lo = padded_planes(r_rows.reshape(-1, 1), g_rows)
         sl = sdf_off + L - 1
-        g_row0 = tn_planes(rr_hi, rr_lo, gs_hi[sl], gs_lo[sl])            # [1,256]
+        g_row0 = tn_planes(rr_hi, rr_lo, gs_hi[sl], gs_lo[sl])[:1]        # [1,256]
         h8p_hi = gs_hi[sl].view(p_g, 4, 256)[:n, 0].contiguous()          # primal rows of the output layer's input
         h8p_lo = gs_lo[sl].view(p_g, 4, 256)[:n, 0].contiguous()
         fb_hi, fb_lo = split16(feat_bar)
@@ -316,7 +324,7 @@ class PointFieldFn(torch.autograd.Function):
                             torch.cat([etx, torch.zeros(n, 3, tt.shape[1], device=dev)], -1)], 1)  # [n,4,52]
             a0_hi, a0_lo = padded_planes(a0, g_rows)
             for m in range(0, L - 1):
-                g_in = tn_planes(zd_hi[m], zd_lo[m], a0_hi, a0_lo) if (m == 0 or m == skip) else None
+                g_in = tn_planes(zd_hi[m], zd_lo[m], a0_hi, a0_lo)[:, :a0.shape[-1]] if (m == 0 or m == skip) else None
                 if m == 0:
                     g = g_in
                 else:
@@ -327,13 +335,13 @@ class PointFieldFn(torch.autograd.Function):
                 gb[0][m] = (rowsum_planes(zd_hi[m], zd_lo[m], prim_g) / s_d)[:out_dims[m]]
             o_rows = torch.cat([xc_bar[:, None, :], jbar.permute(0, 2, 1)], 1)   # [n,4,3]
             or_hi, or_lo = padded_planes(o_rows, g_rows)
-            gw[0][L - 1] = tn_planes(or_hi, or_lo, gs_hi[L - 1], gs_lo[L - 1])
+            gw[0][L - 1] = tn_planes(or_hi, or_lo, gs_hi[L - 1], gs_lo[L - 1])[:3]
             gb[0][L - 1] = xc_bar.sum(0)
 
         grads: List[torch.Tensor] = []
         for net in nets:
             grads += gw[net] + gb[net]
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 def effective_weights(model) -> List[torch.Tensor]:
