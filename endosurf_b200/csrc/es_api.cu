@@ -864,7 +864,7 @@ int es_profile_read(es_ctx* ctx, es_profile* out, void* stream) {
 int es_debug_trace(es_ctx* ctx, int64_t* host_out, int64_t capacity_pairs) {
   // host_out == NULL: arm the trace (next chain launches record into it); else copy out [count, (clock, code)...]
   if (!ctx) return ES_E_BADARG;
-  const size_t bytes = (1 + 2 * 8000) * sizeof(long long);
+  const size_t bytes = (2 + 2 * 8000) * sizeof(long long);
   if (!host_out) {
     if (!ctx->trace_dev) CU(cudaMalloc(&ctx->trace_dev, bytes));
     CU(cudaMemset(ctx->trace_dev, 0, bytes));
@@ -872,7 +872,7 @@ int es_debug_trace(es_ctx* ctx, int64_t* host_out, int64_t capacity_pairs) {
   }
   if (!ctx->trace_dev) return ES_E_BADARG;
   CU(cudaDeviceSynchronize());
-  size_t n = std::min<size_t>(bytes, (1 + 2 * static_cast<size_t>(capacity_pairs)) * sizeof(long long));
+  size_t n = std::min<size_t>(bytes, (2 + 2 * static_cast<size_t>(capacity_pairs)) * sizeof(long long));
   CU(cudaMemcpy(host_out, ctx->trace_dev, n, cudaMemcpyDeviceToHost));
   CU(cudaFree(ctx->trace_dev));
   ctx->trace_dev = nullptr;

@@ -32,19 +32,25 @@ constexpr int N_THREADS = 64 + N_EPI_THREADS;
 constexpr int SM_A_OFF = 0;
 constexpr int SM_W_OFF = SM_A_OFF + NSLOT * SLOT_BYTES;    // 131072
 constexpr int SM_XCH_OFF = SM_W_OFF + NSTAGE * UNIT_BYTES;  // 196608
-constexpr int SM_XCH_BYTES = 2 * NPART * TILE_ROWS * 4 * 4;  // [parity][part][row][4] floats
-constexpr int SM_BAR_OFF = SM_XCH_OFF + SM_XCH_BYTES;
+constexpr int SM_XCH_BYTES = NPART * TILE_ROWS * 4 * 4;      // [part][row][4] floats
+constexpr int SM_BIAS_OFF = SM_XCH_OFF + SM_XCH_BYTES;       // [MAXL + 1][256] fp32: every layer's bias + feat bias
+constexpr int SM_BIAS_BYTES = (MAXL + 1) * HID * 4;
+constexpr int PATCH_LD = 20;                                 // padded row length (floats) of an 8 x 16 patch
+constexpr int PATCH_FLOATS = 8 * PATCH_LD;
+constexpr int SM_PATCH_OFF = SM_BIAS_OFF + SM_BIAS_BYTES;    // per epilogue warp: 2 patches (z|h, act')
+constexpr int SM_PATCH_BYTES = N_EPI_WARPS * 2 * PATCH_FLOATS * 4;
+constexpr int SM_BAR_OFF = SM_PATCH_OFF + SM_PATCH_BYTES;
 constexpr int N_BARS = 2 * NSLOT + 2 * NSTAGE + 4;
 constexpr int SM_TMEM_OFF = SM_BAR_OFF + N_BARS * 8;
 constexpr int SM_TOTAL = SM_TMEM_OFF + 16;
 
 struct Bars {
-  uint64_t* a_full;   // [NSLOT]  epilogue -> MMA   (count N_EPI_THREADS)
+  uint64_t* a_full;   // [NSLOT]  epilogue -> MMA   (count N_EPI_WARPS)
   uint64_t* a_empty;  // [NSLOT]  MMA commit -> epilogue
   uint64_t* w_full;   // [NSTAGE] TMA -> MMA
   uint64_t* w_empty;  // [NSTAGE] MMA commit -> TMA
   uint64_t* d_full;   // [2]      MMA commit -> epilogue
-  uint64_t* d_empty;  // [2]      epilogue -> MMA  (count N_EPI_THREADS)
+  uint64_t* d_empty;  // [2]      epilogue -> MMA  (count N_EPI_WARPS)
 };
 
 // ------------------------------------------------------------------------------------------------ activations
@@ -187,13 +193,17 @@ __device__ __forceinline__ void load_planes(const uint16_t* phi, const uint16_t*
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-// debug pipeline trace (CTA 0 only, off unless ChainIO::trace is set)
-__device__ __forceinline__ void trace_ev(long long* trace, int code) {
-  if (trace != nullptr && blockIdx.x == 0) {
-    unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(trace), 1ull);
-    if (i < 8000) {
-      trace[1 + 2 * i] = clock64();
-      trace[2 + 2 * i] = code;
+// debug pipeline trace (CTA 0 only, off unless ChainIO::trace is set).  Two recorder threads (the MMA issuer and
+// epilogue warp 2 lane 0) write into separate halves of the buffer with private counters: no atomics on the path.
+// layout: trace[0] = MMA count, trace[1] = EPI count, then 4000 (clock, code) pairs each.
+__device__ __forceinline__ void trace_ev(long long* trace, int code, int who = 0, unsigned* counter = nullptr) {
+  if (trace != nullptr && blockIdx.x == 0 && counter != nullptr) {
+    const unsigned i = (*counter)++;
+    if (i < 4000) {
+      long long* base = trace + 2 + who * 8000;
+      base[2 * i] = clock64();
+      base[2 * i + 1] = code;
+      trace[who] = i + 1;
     }
   }
 }
@@ -211,52 +221,100 @@ struct EpiCtx {
   uint32_t xk;  // cross-part exchange counter
   long long* trace;
   bool tr;  // this thread records trace events
+  unsigned tcount;
+  float* patch;  // this warp's two 8 x 16 activation patches (shared memory)
 };
 
 // sum a per-row float4 across the NPART column-part threads of the row (every one of them gets the total)
 __device__ __forceinline__ float4 cross_part_sum(EpiCtx& c, float4 part) {
   float4* xch = reinterpret_cast<float4*>(c.smem + SM_XCH_OFF);
-  const int par = c.xk & 1;
-  ++c.xk;
-  xch[(par * NPART + c.part) * TILE_ROWS + c.row] = part;
+  xch[c.part * TILE_ROWS + c.row] = part;
   named_bar_sync(1, N_EPI_THREADS);
-  float4 t = xch[(par * NPART + 0) * TILE_ROWS + c.row];
+  float4 t = xch[c.row];
 #pragma unroll
   for (int q = 1; q < NPART; ++q) {
-    float4 b = xch[(par * NPART + q) * TILE_ROWS + c.row];
+    float4 b = xch[q * TILE_ROWS + c.row];
     t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
   }
+  named_bar_sync(2, N_EPI_THREADS);  // everyone has read before the buffer is written again
   return t;
 }
 
-// Read this thread's PCOLS columns of 64-col block `blk` of accumulator buffer `buf`, add bias, activate.
-// TANGENT rows (s>0): no bias, multiplied by the primal row's activation derivative (quad shuffle).
+// Read this thread's PCOLS columns of 64-col block `blk` of accumulator buffer `buf`, add bias (row `bias_row` of the
+// smem-staged bias table), activate.  TANGENT rows (s>0): no bias, multiplied by the primal row's activation
+// derivative.
+//  * Softplus + tangents: only 1 lane in 4 is a primal row, so running the exp/log/rcp chain on every lane wastes
+//    3/4 of the MUFU/ALU issue slots.  The 8 primal rows of the warp park their 16 raw values in a per-warp smem patch,
+//    every lane then activates 4 of the 128 values (its own point, columns 4s..4s+3), writes h and act' back, and
+//    reads what its row needs (primal: h, tangent: act').  ~2x fewer instructions than the per-element shuffle form.
+//  * ReLU + tangents: one shuffle of the primal pre-activation per element, then a select.
 template <int ACT, bool TANGENT>
-__device__ __forceinline__ void load_act(EpiCtx& c, int buf, int blk, const float* __restrict__ bias, int s,
-                                         float (&v)[PCOLS]) {
+__device__ __forceinline__ void load_act(EpiCtx& c, int buf, int blk, int bias_row, int s, float (&v)[PCOLS]) {
+  static_assert(PCOLS == 16, "the softplus patch path assigns 4 columns to each of the 4 lanes of a point");
   const int col0 = 64 * blk + PCOLS * c.part;
   const uint32_t taddr = c.tmem_base + (static_cast<uint32_t>(c.row & ~31) << 16) + buf * HID + col0;
   tmem_ld<PCOLS>(taddr, v);
-  // the bias loads overlap the TMEM read
-  float bj[PCOLS];
-  const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+  const float* bias = reinterpret_cast<const float*>(c.smem + SM_BIAS_OFF) + bias_row * HID + col0;
+  if constexpr (TANGENT && ACT == ACT_SOFTPLUS100) {
+    float* zh = c.patch;
+    float* dp = c.patch + PATCH_FLOATS;
+    const int p = c.lane >> 2;
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * s);
+    tmem_ld_wait();
+    if (s == 0) {
 #pragma unroll
-  for (int q = 0; q < PCOLS / 4; ++q) {
-    float4 bb = __ldg(b4 + q);
-    bj[4 * q] = bb.x; bj[4 * q + 1] = bb.y; bj[4 * q + 2] = bb.z; bj[4 * q + 3] = bb.w;
-  }
-  const float bsel = (!TANGENT || s == 0) ? 1.f : 0.f;
-  tmem_ld_wait();
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(zh + p * PATCH_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    __syncwarp();
+    const float4 z4 = *reinterpret_cast<const float4*>(zh + p * PATCH_LD + 4 * s);
+    float hh[4], dd[4];
+    activate<ACT>(z4.x + b4.x, hh[0], dd[0]);
+    activate<ACT>(z4.y + b4.y, hh[1], dd[1]);
+    activate<ACT>(z4.z + b4.z, hh[2], dd[2]);
+    activate<ACT>(z4.w + b4.w, hh[3], dd[3]);
+    *reinterpret_cast<float4*>(zh + p * PATCH_LD + 4 * s) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<float4*>(dp + p * PATCH_LD + 4 * s) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+    __syncwarp();
+    const float* src = (s == 0 ? zh : dp) + p * PATCH_LD;
 #pragma unroll
-  for (int i = 0; i < PCOLS; ++i) {
-    float z = fmaf(bj[i], bsel, v[i]);
-    float h, dh;
-    activate<ACT>(z, h, dh);
-    if (TANGENT) {
-      float dhp = __shfl_sync(0xffffffffu, dh, c.lane & ~3);
-      v[i] = (s == 0) ? h : dhp * v[i];
+    for (int q = 0; q < 4; ++q) {
+      const float4 r = *reinterpret_cast<const float4*>(src + 4 * q);
+      v[4 * q + 0] = (s == 0) ? r.x : r.x * v[4 * q + 0];
+      v[4 * q + 1] = (s == 0) ? r.y : r.y * v[4 * q + 1];
+      v[4 * q + 2] = (s == 0) ? r.z : r.z * v[4 * q + 2];
+      v[4 * q + 3] = (s == 0) ? r.w : r.w * v[4 * q + 3];
+    }
+    __syncwarp();  // the patch is rewritten by the next call
+  } else {
+    float bj[PCOLS];
+#pragma unroll
+    for (int q = 0; q < PCOLS / 4; ++q) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * q);
+      bj[4 * q] = bb.x; bj[4 * q + 1] = bb.y; bj[4 * q + 2] = bb.z; bj[4 * q + 3] = bb.w;
+    }
+    tmem_ld_wait();
+    if constexpr (TANGENT && ACT == ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < PCOLS; ++i) {
+        const float zp = __shfl_sync(0xffffffffu, v[i] + bj[i], c.lane & ~3);  // primal pre-activation
+        const float w = (s == 0) ? zp : v[i];
+        v[i] = zp > 0.f ? w : 0.f;
+      }
     } else {
-      v[i] = h;
+      const float bsel = (!TANGENT || s == 0) ? 1.f : 0.f;
+#pragma unroll
+      for (int i = 0; i < PCOLS; ++i) {
+        float z = fmaf(bj[i], bsel, v[i]);
+        float h, dh;
+        activate<ACT>(z, h, dh);
+        if (TANGENT) {
+          float dhp = __shfl_sync(0xffffffffu, dh, c.lane & ~3);
+          v[i] = (s == 0) ? h : dhp * v[i];
+        } else {
+          v[i] = h;
+        }
+      }
     }
   }
 }
@@ -304,7 +362,7 @@ __device__ __forceinline__ void bwd_gate(EpiCtx& c, const uint16_t* shi, const u
 }
 
 template <bool TANGENT>
-__device__ __forceinline__ void load_act_dyn(EpiCtx& c, int act, int buf, int blk, const float* bias, int s,
+__device__ __forceinline__ void load_act_dyn(EpiCtx& c, int act, int buf, int blk, int bias, int s,
                                              float (&v)[PCOLS]) {
   if (act == ACT_RELU) load_act<ACT_RELU, TANGENT>(c, buf, blk, bias, s, v);
   else if (act == ACT_SOFTPLUS100) load_act<ACT_SOFTPLUS100, TANGENT>(c, buf, blk, bias, s, v);
@@ -334,17 +392,18 @@ __device__ __forceinline__ void dot_accum(const float (&v)[PCOLS], const float* 
 __device__ __forceinline__ void wait_d_full(EpiCtx& c, uint32_t g_layer) {
   mbar_wait(&c.bars.d_full[g_layer & 1], (g_layer >> 1) & 1, c.err, 100 + static_cast<int>(g_layer & 1));
   tc_fence_after();
-  if (c.tr) trace_ev(c.trace, 4000 + static_cast<int>(g_layer % 100));  // EPI: accumulator of layer g ready
+  if (c.tr) trace_ev(c.trace, 4000 + static_cast<int>(g_layer % 100), 1, &c.tcount);  // EPI: accumulator of layer g ready
 }
 __device__ __forceinline__ void release_d(EpiCtx& c, uint32_t g_layer) {
   tc_fence_before();
-  mbar_arrive(&c.bars.d_empty[g_layer & 1]);
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(&c.bars.d_empty[g_layer & 1]);
 }
 
 // Consume the whole accumulator of global layer g_layer through a NOUT-wide fp32 output layer (no MMA):
 // out = W_out . act(D + bias) summed over both column halves.  Returns the cross-half total in .x/.y/.z.
 template <int NOUT, bool TANGENT>
-__device__ __forceinline__ float4 tail_dot(EpiCtx& c, uint32_t g_layer, int act, const float* bias,
+__device__ __forceinline__ float4 tail_dot(EpiCtx& c, uint32_t g_layer, int act, int bias,
                                            const float* w_out, int s, uint16_t* st_hi = nullptr,
                                            uint16_t* st_lo = nullptr) {
   wait_d_full(c, g_layer);
@@ -394,7 +453,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) {
-      mbar_init(&bars.a_full[i], N_EPI_THREADS);
+      mbar_init(&bars.a_full[i], N_EPI_WARPS);   // one elected arrive per epilogue warp
       mbar_init(&bars.a_empty[i], 1);
     }
     for (int i = 0; i < NSTAGE; ++i) {
@@ -403,11 +462,16 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.d_full[i], 1);
-      mbar_init(&bars.d_empty[i], N_EPI_THREADS);
+      mbar_init(&bars.d_empty[i], N_EPI_WARPS);
     }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if constexpr (!BWD) {  // stage every layer's bias (+ the feature-layer bias in row MAXL) in shared memory
+    float* bs = reinterpret_cast<float*>(smem + SM_BIAS_OFF);
+    for (int i = threadIdx.x; i < prog.n_layers * HID; i += N_THREADS) bs[i] = __ldg(prog.bias + i);
+    for (int i = threadIdx.x; i < HID; i += N_THREADS) bs[MAXL * HID + i] = __ldg(prog.feat_out_b + i);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -445,6 +509,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(TILE_ROWS, HID);
       uint32_t wc = 0, ac = 0, g = 0;
+      unsigned tcount = 0;
       const uint64_t a_desc0 = make_smem_desc(smem_u32(smem + SM_A_OFF), A_LBO, A_SBO);
       const uint64_t w_desc0 = make_smem_desc(smem_u32(smem + SM_W_OFF), B_LBO, B_SBO);
       constexpr uint64_t A_KS = (2 * A_LBO) >> 4;          // one K=16 step inside a slot plane
@@ -460,14 +525,14 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           const uint32_t d_tmem = tmem_base + (g & 1) * HID;
           mbar_wait(&bars.d_empty[g & 1], ((g >> 1) & 1) ^ 1, err, 300 + static_cast<int>(g & 1));
           tc_fence_after();
-          trace_ev(io.trace, 1000 + l);  // MMA: accumulator free, layer l starts
+          trace_ev(io.trace, 1000 + l, 0, &tcount);  // MMA: accumulator free, layer l starts
           uint32_t accum = 0;
           for (int ck = 0; ck < n_chunks; ++ck, ++ac) {
             const uint32_t slot = ac % NSLOT;
             const int nsub = L.nsub[ck];
             mbar_wait(&bars.a_full[slot], (ac / NSLOT) & 1, err, 310);
             tc_fence_after();
-            trace_ev(io.trace, 2000 + l * 16 + ck);  // MMA: chunk ck of layer l available
+            trace_ev(io.trace, 2000 + l * 16 + ck, 0, &tcount);  // MMA: chunk ck of layer l available
             uint64_t a_hi = a_desc0 + static_cast<uint64_t>(slot * (SLOT_BYTES >> 4));
             for (int sb = 0; sb < nsub; ++sb, a_hi += A_SB) {
               // ---- hi weight unit: A_hi*B_hi and A_lo*B_hi
@@ -503,7 +568,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
             umma_commit(&bars.a_empty[slot]);
           }
           umma_commit(&bars.d_full[g & 1]);
-          trace_ev(io.trace, 3000 + l);  // MMA: all MMAs of layer l issued
+          trace_ev(io.trace, 3000 + l, 0, &tcount);  // MMA: all MMAs of layer l issued
         }
       }
     }
@@ -520,8 +585,10 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
     c.ac = 0;
     c.g = 0;
     c.xk = 0;
+    c.patch = reinterpret_cast<float*>(smem + SM_PATCH_OFF) + (warp - 2) * 2 * PATCH_FLOATS;
     c.trace = io.trace;
     c.tr = (warp == 2 && lane == 0);
+    c.tcount = 0;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       // ---------------------------------------------------------- row state
@@ -576,7 +643,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
 
       for (int l = 0; l < prog.n_layers; ++l, ++c.g) {
         const LayerProg& L = prog.layer[l];
-        const float* bias_prev = prog.bias + static_cast<size_t>(l > 0 ? l - 1 : 0) * HID;
+        const int bias_prev = l > 0 ? l - 1 : 0;  // row of the smem bias table
         const int act_prev = l > 0 ? prog.layer[l - 1].act : ACT_NONE;
         bool prev_waited = false;
 
@@ -616,7 +683,10 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
 
         for (int ck = 0; ck < L.n_chunks; ++ck, ++c.ac) {
           const uint32_t slot = c.ac % NSLOT;
-          mbar_wait(&bars.a_empty[slot], ((c.ac / NSLOT) & 1) ^ 1, err, 400);
+          // Every layer starts after the previous layer's accumulator is complete, i.e. after every earlier MMA has
+          // read its A slot: the first NSLOT chunks of a layer never have to wait for a free slot.
+          if (ck >= NSLOT) mbar_wait(&bars.a_empty[slot], ((c.ac / NSLOT) & 1) ^ 1, err, 400);
+          if (c.tr) trace_ev(io.trace, 6000 + l * 16 + ck, 1, &c.tcount);  // EPI: slot free
           uint8_t* slot_base = smem + SM_A_OFF + slot * SLOT_BYTES;
           float v[PCOLS];
           const int src = L.src[ck];
@@ -690,10 +760,14 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
               v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
             }
           }
+          if (c.tr) trace_ev(io.trace, 7000 + l * 16 + ck, 1, &c.tcount);  // EPI: values ready (tmem + math done)
           if (active) emit_part((io.debug_flags & 2) ? nullptr : slot_base, c.row, c.part, v, dump_hi, dump_lo);
+          if (c.tr) trace_ev(io.trace, 8000 + l * 16 + ck, 1, &c.tcount);  // EPI: stores issued
           fence_proxy_async_smem();
-          mbar_arrive(&bars.a_full[slot]);
-          if (c.tr) trace_ev(io.trace, 5000 + l * 16 + ck);  // EPI: chunk ck of layer l written
+          if (c.tr) trace_ev(io.trace, 9000 + l * 16 + ck, 1, &c.tcount);  // EPI: proxy fence done
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.a_full[slot]);  // 512 same-word arrivals serialise; 16 do not
+          if (c.tr) trace_ev(io.trace, 5000 + l * 16 + ck, 1, &c.tcount);  // EPI: chunk ck of layer l written
         }
 
         if (L.side_dot) {
@@ -711,7 +785,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
 
       // ---------------------------------------------------------- post op: consume the last accumulator
       const int last = prog.n_layers - 1;
-      const float* bias_last = prog.bias + static_cast<size_t>(last) * HID;
+      const int bias_last = last;
       const int act_last = prog.layer[last].act;
       if (prog.post_op == POST_SDF_TAIL) {
         float4 r = tail_dot<1, TANGENT>(c, c.g - 1, act_last, bias_last, prog.sdf_out_w, rs.s);
@@ -753,7 +827,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         for (int blk = 0; blk < 4; ++blk) {
           float v[PCOLS];
           // feat = D + bias (no activation); tangent rows are not needed
-          load_act<ACT_NONE, false>(c, (c.g - 1) & 1, blk, prog.feat_out_b, 0, v);
+          load_act<ACT_NONE, false>(c, (c.g - 1) & 1, blk, MAXL, 0, v);  // row MAXL = feature-layer bias
           if (rs.valid && rs.s == 0) {
             float4* o4 = reinterpret_cast<float4*>(io.out_feat + rs.pt * HID + 64 * blk + PCOLS * c.part);
 #pragma unroll

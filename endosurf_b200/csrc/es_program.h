@@ -14,7 +14,7 @@ constexpr int SLOT_HALF_BYTES = TILE_ROWS * CHUNK_K * 2;  // 16 KiB: hi or lo pl
 constexpr int SLOT_BYTES = 2 * SLOT_HALF_BYTES;           // 32 KiB
 constexpr int NSLOT = 3;
 constexpr int UNIT_BYTES = HID * SUB_K * 2;               // 16 KiB: 256 x 32 fp16 (hi or lo)
-constexpr int NSTAGE = 6;
+constexpr int NSTAGE = 4;
 // canonical no-swizzle K-major layout: [k-group of 8][row][8 elements]
 constexpr int A_LBO = TILE_ROWS * 16;  // 2048  bytes between K core matrices
 constexpr int A_SBO = 128;             //        bytes between 8-row groups

@@ -13,11 +13,14 @@ fn = (lambda: r.sdf_from_observed_space(x, t)) if which == "sdfq" else (lambda: 
 fn(); torch.cuda.synchronize()
 lib.es_debug_trace(ctx, None, 0)
 fn(); torch.cuda.synchronize()
-buf = np.zeros(1 + 2 * 8000, dtype=np.int64)
+buf = np.zeros(2 + 2 * 8000, dtype=np.int64)
 lib.es_debug_trace(ctx, buf.ctypes.data_as(C.c_void_p), 8000)
-cnt = int(min(buf[0], 8000)); ev = buf[1:1 + 2 * cnt].reshape(-1, 2)
+n0, n1 = int(min(buf[0], 4000)), int(min(buf[1], 4000))
+ev = np.concatenate([buf[2:2 + 2 * n0].reshape(-1, 2), buf[2 + 8000:2 + 8000 + 2 * n1].reshape(-1, 2)])
+cnt = n0 + n1
 ev = ev[np.argsort(ev[:, 0])]; t0 = ev[0, 0]
-names = {1: "MMA layer start", 2: "MMA chunk ready", 3: "MMA layer issued", 4: "EPI acc ready", 5: "EPI chunk written"}
+names = {1: "MMA layer start", 2: "MMA chunk ready", 3: "MMA layer issued", 4: "EPI acc ready", 5: "EPI chunk written",
+         6: "EPI  slot free", 7: "EPI  values ready", 8: "EPI  stores issued", 9: "EPI  fence done"}
 print("events", cnt)
 last = {}
 for clk, code in ev[:400]:
