@@ -206,6 +206,7 @@ void build_net_plan(const es_net_config& cfg, int net, NetPlan& P) {
       G.side_dot = 1;
     }
     G.n_chunks = static_cast<uint8_t>(nc);
+    finish_layer(G);
     K.k_total = static_cast<int>(K.colmap.size());
   }
 }
@@ -306,6 +307,7 @@ void build_chain_programs(es_ctx* ctx) {
     G.zbar_slot = static_cast<uint8_t>(zbar_slot);
     G.bwd_act = act;
     G.rank1 = rank1 ? 1 : 0;
+    finish_layer(G);
   };
   for (int net = 0; net < 3; ++net) {
     ChainProg r{};

@@ -118,6 +118,17 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]) {
   if constexpr (N == 16) tmem_ld16(taddr, v);
   else tmem_ld32(taddr, v);
 }
+// 16 lanes x 256 bit (x2 = 16 columns): thread t of the warp receives, for TMEM lanes L = base_lane + t/4 and L + 8
+// and column pairs c = col + 2*(t%4) + {0,1} and c + 8:   r0,r1 = (L, c..c+1)   r2,r3 = (L+8, c..c+1)
+//                                                          r4,r5 = (L, c+8..c+9) r6,r7 = (L+8, c+8..c+9)
+// (the m16n8 accumulator-fragment layout; cute SM100_TMEM_LOAD_16dp256b2x).  base_lane = 32*(warp%4) or that + 16.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float& r0, float& r1, float& r2, float& r3,
+                                                   float& r4, float& r5, float& r6, float& r7) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3), "=f"(r4), "=f"(r5), "=f"(r6), "=f"(r7)
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ UMMA descriptors (see cute/arch/mma_sm100_desc.hpp

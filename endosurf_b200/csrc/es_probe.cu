@@ -71,6 +71,24 @@ umma_probe_kernel(const uint16_t* __restrict__ a, const uint8_t* __restrict__ b_
     tmem_ld_wait();
     for (int i = 0; i < 32; ++i) d[(warp * 32 + lane) * 256 + blk * 32 + i] = v[i];
   }
+  // mode bit 8: read back through the 16x256b fragment shape (both 16-lane halves of the warp's quadrant)
+  for (int blk = 0; blk < 16 && (mode & 8); ++blk) {
+    for (int half = 0; half < 2; ++half) {
+      float r[8];
+      tmem_ld_16x256b_x2(tmem_base + (static_cast<uint32_t>(warp * 32 + 16 * half) << 16) + blk * 16, r[0], r[1], r[2],
+                         r[3], r[4], r[5], r[6], r[7]);
+      tmem_ld_wait();
+      const int row = warp * 32 + 16 * half + (lane >> 2), col = blk * 16 + 2 * (lane & 3);
+      d[row * 256 + col] = r[0];
+      d[row * 256 + col + 1] = r[1];
+      d[(row + 8) * 256 + col] = r[2];
+      d[(row + 8) * 256 + col + 1] = r[3];
+      d[row * 256 + col + 8] = r[4];
+      d[row * 256 + col + 9] = r[5];
+      d[(row + 8) * 256 + col + 8] = r[6];
+      d[(row + 8) * 256 + col + 9] = r[7];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem_base);

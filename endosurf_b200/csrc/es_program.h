@@ -12,7 +12,7 @@ constexpr int CHUNK_K = 64;        // K extent of one A-operand ring slot
 constexpr int SUB_K = 32;          // K extent of one weight unit
 constexpr int SLOT_HALF_BYTES = TILE_ROWS * CHUNK_K * 2;  // 16 KiB: hi or lo plane of a slot
 constexpr int SLOT_BYTES = 2 * SLOT_HALF_BYTES;           // 32 KiB
-constexpr int NSLOT = 3;
+constexpr int NSLOT = 4;            // A-operand ring slots (power of two): a whole 256-wide layer input fits
 constexpr int UNIT_BYTES = HID * SUB_K * 2;               // 16 KiB: 256 x 32 fp16 (hi or lo)
 constexpr int NSTAGE = 4;
 // canonical no-swizzle K-major layout: [k-group of 8][row][8 elements]
@@ -46,6 +46,7 @@ struct LayerProg {
   uint8_t act;       // activation of THIS layer's output (applied by the consumer of its accumulator)
   uint8_t pre_op;    // epilogue work before this layer's first chunk
   uint8_t side_dot;  // 1: while converting the previous layer's output also accumulate the sdf row
+  uint8_t last_prev; // index of the last chunk that reads the previous accumulator (SRC_PREV / SRC_BWD_PREV), 0xFF: none
   uint8_t src[MAXC];
   uint8_t arg[MAXC];
   uint8_t nsub[MAXC];  // number of 32-wide K sub-blocks in the chunk that carry weights (1 or 2)
@@ -55,6 +56,13 @@ struct LayerProg {
   uint8_t bwd_act;     // activation being differentiated (ACT_RELU / ACT_SOFTPLUS100)
   uint8_t rank1;       // 1: add adj.w * sdf_out_w[col] to the incoming adjoint (sdf row of the output layer)
 };
+
+// host helper: fill LayerProg::last_prev after the chunk list is complete
+inline void finish_layer(LayerProg& g) {
+  g.last_prev = 0xFF;
+  for (int k = 0; k < g.n_chunks; ++k)
+    if (g.src[k] == SRC_PREV || g.src[k] == SRC_BWD_PREV) g.last_prev = static_cast<uint8_t>(k);
+}
 
 struct ChainProg {
   int32_t n_layers;

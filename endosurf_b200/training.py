@@ -55,6 +55,19 @@ def planes_f32(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
     return hi.view(torch.float16).float() + lo.view(torch.float16).float()
 
 
+def rows_from_points(v: torch.Tensor) -> torch.Tensor:
+    """[p_g, 4, k] (point, stream) -> [4 p_g, k] in the geometry kernels' tile row order: a 128-row tile holds 32
+    points; stream s of point (quadrant Q, p) is tile row 32 Q + 8 s + p (csrc/es_mlp.cu, tangent mode)."""
+    pg = v.shape[0]
+    return v.reshape(pg // 32, 4, 8, 4, -1).permute(0, 1, 3, 2, 4).reshape(pg * 4, -1)
+
+
+def points_from_rows(r: torch.Tensor) -> torch.Tensor:
+    """Inverse of :func:`rows_from_points`: [rows, k] -> [rows / 4, 4, k]."""
+    rows = r.shape[0]
+    return r.reshape(rows // 128, 4, 4, 8, -1).permute(0, 1, 3, 2, 4).reshape(rows // 4, 4, -1)
+
+
 _MM_OUT_DTYPE_OK = None
 FAST_MIN_ROWS = 32768  # below this the exact fp32 product is cheap (tests); above, fp16 tensor-core library GEMMs
 
@@ -201,9 +214,9 @@ class PointFieldFn(torch.autograd.Function):
         f16 = torch.float16
         # 0/1 row selectors for bias gradients (tangent rows carry no bias)
         ones_c = torch.ones(1, c_rows, dtype=f16, device=dev)
-        prim_g = torch.zeros(p_g, 4, dtype=f16, device=dev)
+        prim_g = torch.zeros(p_g, 4, 1, dtype=f16, device=dev)
         prim_g[:, 0] = 1
-        prim_g = prim_g.reshape(1, g_rows)
+        prim_g = rows_from_points(prim_g).reshape(1, g_rows)
 
         def run_reverse(net, adj, adj_feat, stash_hi, stash_lo, rows):
             zb_hi = torch.empty(z_slots, rows, 256, dtype=torch.int16, device=dev)
@@ -214,9 +227,13 @@ class PointFieldFn(torch.autograd.Function):
             return zb_hi, zb_lo
 
         def padded_planes(v, rows):
-            """[n, k] fp32 (per point) or [n, 4, k] (per row) -> hi/lo planes zero-padded to the stash row count."""
-            v = v.reshape(-1, v.shape[-1])
-            cols = (v.shape[1] + 15) // 16 * 16   # odd widths push cuBLAS onto legacy kernels
+            """[n, k] fp32 (plain chains: row = point) or [n, 4, k] (geometry chains: 4 streams per point, kernel
+            tile row order) -> hi/lo planes zero-padded to the stash row count."""
+            cols = (v.shape[-1] + 15) // 16 * 16   # odd widths push cuBLAS onto legacy kernels
+            if v.dim() == 3:
+                buf = torch.zeros(rows // 4, 4, cols, device=dev)
+                buf[:v.shape[0], :, :v.shape[-1]] = v
+                return split16(rows_from_points(buf))
             buf = torch.zeros(rows, cols, device=dev)
             buf[:v.shape[0], :v.shape[1]] = v
             return split16(buf)
@@ -283,7 +300,7 @@ class PointFieldFn(torch.autograd.Function):
             E = None
             for m in range(0, L - 1):
                 if m == 0 or m == skip:
-                    Zp = planes_f32(zs_hi[m], zs_lo[m]).view(p_g, 4, 256)[:n]
+                    Zp = points_from_rows(planes_f32(zs_hi[m], zs_lo[m]))[:n]
                     w_in = Ws[0] if m == 0 else Ws[m][:, 256:] / SQRT2
                     E = Zp @ w_in if E is None else E + Zp @ w_in            # adjoint of the input rows [n,4,39]
                 g_in = tn_planes(zs_hi[m], zs_lo[m], a0_hi, a0_lo)[:, :a0.shape[-1]] if (m == 0 or m == skip) else None
@@ -297,11 +314,11 @@ class PointFieldFn(torch.autograd.Function):
                 gb[1][m] = rowsum_planes(zs_hi[m], zs_lo[m], prim_g) / s_s
             xc_bar = xc_bar + torch.autograd.grad((a0 * (E / s_s).detach()).sum(), xc_r)[0]
         r_rows = torch.cat([sdf_bar, gc_tot], 1)                          # [n,4]: adjoint of the sdf-row output
-        rr_hi, rr_lo = padded_planes(r_rows.reshape(-1, 1), g_rows)
+        rr_hi, rr_lo = padded_planes(r_rows.reshape(n, 4, 1), g_rows)
         sl = sdf_off + L - 1
         g_row0 = tn_planes(rr_hi, rr_lo, gs_hi[sl], gs_lo[sl])[:1]        # [1,256]
-        h8p_hi = gs_hi[sl].view(p_g, 4, 256)[:n, 0].contiguous()          # primal rows of the output layer's input
-        h8p_lo = gs_lo[sl].view(p_g, 4, 256)[:n, 0].contiguous()
+        h8p_hi = points_from_rows(gs_hi[sl])[:n, 0].contiguous()          # primal rows of the output layer's input
+        h8p_lo = points_from_rows(gs_lo[sl])[:n, 0].contiguous()
         fb_hi, fb_lo = split16(feat_bar)
         gw[1][L - 1] = torch.cat([g_row0, tn_planes(fb_hi, fb_lo, h8p_hi, h8p_lo)], 0)
         gb[1][L - 1] = torch.cat([sdf_bar.sum(0), feat_bar.sum(0)], 0)

@@ -5,6 +5,7 @@ Tolerances (north_star: 1e-4 relative fp32): per-ray integrals and smooth per-po
 max|a-b| / max|b| <= 1e-4.  Quantities that contain derivatives of the ReLU deformation network (Jacobian, g_o,
 gradients_o) are discontinuous at ReLU kinks, so they use the kink-tolerant check of conftest.assert_close."""
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -55,6 +56,18 @@ def test_umma_probe_layout():
     # (confirmed on B200: LBO = byte stride between the two K core matrices, SBO = stride between 8-row groups;
     #  the swapped convention reads out of the shared-memory window and faults)
     assert rel_err(d, ref) < 1e-5, "UMMA descriptor convention wrong"
+    # the tangent-mode epilogue reads the accumulator through the 16x256b fragment shape (4 rows of a point per thread)
+    os.environ["ES_PROBE_MODE"] = "11"
+    try:
+        d2 = torch.zeros(128, 256, device="cuda")
+        rc = lib.es_umma_probe(ctx, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(d2.data_ptr()),
+                               0, 0, 0, 0, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        r.sync_check()
+    finally:
+        del os.environ["ES_PROBE_MODE"]
+    assert rel_err(d2, ref) < 1e-5, "16x256b TMEM fragment layout differs from the documented one"
 
 
 def test_sdf_query_stage(cfg, ckpt):
