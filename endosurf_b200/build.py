@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", s, "-o", o]
+            cmd = [nvcc, *ARCH, *COMMON, *extra, *os.environ.get("ES_NVCC_FLAGS", "").split(), "-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             log = r.stdout + r.stderr
             with open(o + ".log", "w") as f:

@@ -44,18 +44,70 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Returns false if the watchdog tripped (the caller keeps going; results are garbage and the
-// error word tells the host).  `err` points to a global int; `code` identifies the wait site.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+// Slow path of mbar_wait, kept out of line so that the hot loops only carry the try_wait + branch.  Returns false if
+// the watchdog tripped (the caller keeps going; results are garbage and the error word tells the host).  `err` points
+// to a global int; `code` identifies the wait site.
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar_sa, uint32_t parity, int* err, int code) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_sa), "r"(parity)
+        : "memory");
+    if (ok) return true;
     if (++spins > ES_WATCHDOG_SPINS) {
       atomicCAS(err, 0, code);
       return false;
     }
     if ((spins & 0xFFFF) == 0 && *reinterpret_cast<volatile int*>(err) != 0) return false;
   }
-  return true;
+}
+__device__ __forceinline__ bool mbar_wait_sa(uint32_t bar_sa, uint32_t parity, int* err, int code) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_sa), "r"(parity)
+      : "memory");
+  if (ok) return true;
+  return mbar_wait_slow(bar_sa, parity, err, code);
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  return mbar_wait_sa(smem_u32(bar), parity, err, code);
+}
+__device__ __forceinline__ void mbar_arrive_sa(uint32_t bar_sa) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_sa) : "memory");
+}
+
+// ------------------------------------------------------------------ shared-memory stores by 32-bit shared address
+template <int OFF>
+__device__ __forceinline__ void sts32(uint32_t sa, uint32_t v) {
+  asm volatile("st.shared.b32 [%0+%1], %2;" ::"r"(sa), "n"(OFF), "r"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts64(uint32_t sa, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0+%1], {%2, %3};" ::"r"(sa), "n"(OFF), "r"(a), "r"(b) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts128(uint32_t sa, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0+%1], {%2, %3, %4, %5};" ::"r"(sa), "n"(OFF), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ float2 lds64f(uint32_t sa) {
+  float2 r;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(sa));
+  return r;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t sa) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sa));
+  return r;
 }
 
 // ------------------------------------------------------------------ proxies / fences

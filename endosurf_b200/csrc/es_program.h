@@ -12,9 +12,15 @@ constexpr int CHUNK_K = 64;        // K extent of one A-operand ring slot
 constexpr int SUB_K = 32;          // K extent of one weight unit
 constexpr int SLOT_HALF_BYTES = TILE_ROWS * CHUNK_K * 2;  // 16 KiB: hi or lo plane of a slot
 constexpr int SLOT_BYTES = 2 * SLOT_HALF_BYTES;           // 32 KiB
-constexpr int NSLOT = 4;            // A-operand ring slots (power of two): a whole 256-wide layer input fits
+#ifndef ES_NSLOT
+#define ES_NSLOT 3
+#endif
+#ifndef ES_NSTAGE
+#define ES_NSTAGE 6
+#endif
+constexpr int NSLOT = ES_NSLOT;     // A-operand ring slots (32 KiB each)
 constexpr int UNIT_BYTES = HID * SUB_K * 2;               // 16 KiB: 256 x 32 fp16 (hi or lo)
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = ES_NSTAGE;  // weight ring stages (16 KiB each): must cover L2 latency x 43 B/clk (>= 6)
 // canonical no-swizzle K-major layout: [k-group of 8][row][8 elements]
 constexpr int A_LBO = TILE_ROWS * 16;  // 2048  bytes between K core matrices
 constexpr int A_SBO = 128;             //        bytes between 8-row groups
