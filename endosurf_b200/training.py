@@ -69,6 +69,12 @@ def points_from_rows(r: torch.Tensor) -> torch.Tensor:
 
 
 _MM_OUT_DTYPE_OK = None
+# fp16 hi/lo terms of the weight-gradient GEMMs.  1 = zbar_hi^T @ stash_hi with fp32 accumulation: the rounding of the
+# individual products (2^-11) averages out over the >= 10^5 rows of a batch - measured on a 1024-ray batch against
+# exact fp32 products: whole-gradient deviation 6.7e-5, worst parameter tensor 1.6e-4 (3 terms: 2.5e-5 / 4e-5, which
+# is the fp32 summation noise of the comparison itself; tools/wgrad_terms_check.py).  The forward pass and the
+# activation-gradient chains keep the full 3-term products.
+WGRAD_TERMS = 1
 FAST_MIN_ROWS = 32768  # below this the exact fp32 product is cheap (tests); above, fp16 tensor-core library GEMMs
 
 
@@ -93,13 +99,35 @@ def tn_planes(a_hi, a_lo, b_hi, b_lo) -> torch.Tensor:
         try:
             at_h, at_l = ah.t(), al.t()
             out = _mm16(at_h, bh)
-            out += _mm16(at_h, bl)
-            out += _mm16(at_l, bh)
+            if WGRAD_TERMS >= 2:
+                out += _mm16(at_h, bl)
+            if WGRAD_TERMS >= 3:
+                out += _mm16(at_l, bh)
             _MM_OUT_DTYPE_OK = True
             return out
         except (TypeError, RuntimeError):
             _MM_OUT_DTYPE_OK = False
     return (ah.float() + al.float()).t() @ (bh.float() + bl.float())
+
+
+def planes_mm(a_hi, a_lo, w: torch.Tensor) -> torch.Tensor:
+    """A @ w for A [rows, 256] held as fp16 hi/lo planes and a small fp32 w [256, k] -> [rows, k] fp32 (input-layer
+    adjoints).  Large row counts: hi@w_hi + hi@w_lo + lo@w_hi on the tensor cores; small ones: the exact product."""
+    ah, al = a_hi.view(torch.float16), a_lo.view(torch.float16)
+    k = w.shape[1]
+    if ah.shape[0] >= FAST_MIN_ROWS and _MM_OUT_DTYPE_OK is not False:
+        kp = (k + 15) // 16 * 16
+        wp = torch.zeros(w.shape[0], kp, device=w.device)
+        wp[:, :k] = w
+        wh, wl = split16(wp)
+        try:
+            out = _mm16(ah, wh)
+            out += _mm16(ah, wl)
+            out += _mm16(al, wh)
+            return out[:, :k]
+        except (TypeError, RuntimeError):
+            pass
+    return (ah.float() + al.float()) @ w
 
 
 def rowsum_planes(hi, lo, sel16: torch.Tensor) -> torch.Tensor:
@@ -251,9 +279,9 @@ class PointFieldFn(torch.autograd.Function):
         inp_bar = None
         for m in range(0, L - 1):
             if m == 0 or m == skip:  # layers that read the network input: need zbar itself for the input adjoint
-                Zm = planes_f32(zc_hi[m], zc_lo[m])[:n]
                 w_in = Wc[0] if m == 0 else Wc[m][:, 256:] / SQRT2
-                inp_bar = Zm @ w_in if inp_bar is None else inp_bar + Zm @ w_in
+                ib = planes_mm(zc_hi[m], zc_lo[m], w_in)[:n]
+                inp_bar = ib if inp_bar is None else inp_bar + ib
             g_in = tn_planes(zc_hi[m], zc_lo[m], inp_hi, inp_lo)[:, :inp_c.shape[1]] if (m == 0 or m == skip) else None
             if m == 0:
                 g = g_in
@@ -300,9 +328,9 @@ class PointFieldFn(torch.autograd.Function):
             E = None
             for m in range(0, L - 1):
                 if m == 0 or m == skip:
-                    Zp = points_from_rows(planes_f32(zs_hi[m], zs_lo[m]))[:n]
                     w_in = Ws[0] if m == 0 else Ws[m][:, 256:] / SQRT2
-                    E = Zp @ w_in if E is None else E + Zp @ w_in            # adjoint of the input rows [n,4,39]
+                    Em = points_from_rows(planes_mm(zs_hi[m], zs_lo[m], w_in))[:n]
+                    E = Em if E is None else E + Em                          # adjoint of the input rows [n,4,39]
                 g_in = tn_planes(zs_hi[m], zs_lo[m], a0_hi, a0_lo)[:, :a0.shape[-1]] if (m == 0 or m == skip) else None
                 if m == 0:
                     g = g_in

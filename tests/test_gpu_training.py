@@ -135,3 +135,38 @@ def test_training_step_changes_loss(cfg, ckpt):
     r.sync_check()
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0]
+
+
+def test_plane_gemm_fast_paths():
+    """The tensor-core library GEMMs the training glue uses above FAST_MIN_ROWS (the unit batches above are below it)
+    against float64 products of the same hi/lo planes."""
+    from endosurf_b200 import training as T
+    g = torch.Generator().manual_seed(5)
+    rows = 2 * T.FAST_MIN_ROWS
+    a = (torch.randn(rows, 256, generator=g) * torch.rand(rows, 1, generator=g)).cuda()
+    b = torch.randn(rows, 256, generator=g).cuda()
+    (ah, al), (bh, bl) = T.split16(a), T.split16(b)
+    a64 = ah.double() + al.double()
+    b64 = bh.double() + bl.double()
+    ref = a64.t() @ b64
+    old = T.WGRAD_TERMS
+    try:
+        # 3 terms: products exact to 2^-22, the rest is the fp32 (split-K) accumulation over 65536 rows
+        for terms, tol in ((3, 2e-5), (1, 1e-3)):
+            T.WGRAD_TERMS = terms
+            out = T.tn_planes(ah, al, bh, bl)
+            assert T._MM_OUT_DTYPE_OK, "fp16 GEMM with fp32 output is not available: the fast path did not run"
+            e = ((out.double() - ref).norm() / ref.norm()).item()
+            assert e < tol, f"tn_planes terms={terms}: rel err {e:.3e}"
+    finally:
+        T.WGRAD_TERMS = old
+    w = torch.randn(256, 39, generator=g).cuda()
+    out = T.planes_mm(ah, al, w)
+    ref = a64 @ w.double()
+    e = ((out.double() - ref).norm() / ref.norm()).item()
+    assert e < 2e-5, f"planes_mm: rel err {e:.3e}"
+    sel = (torch.rand(1, rows, generator=g) < 0.25).to(torch.float16).cuda()
+    out = T.rowsum_planes(ah, al, sel)
+    ref = (sel.double() @ a64)[0]
+    e = ((out.double() - ref).norm() / ref.norm()).item()
+    assert e < 2e-5, f"rowsum_planes: rel err {e:.3e}"

@@ -1,7 +1,17 @@
-"""Pipeline trace of one CTA of a fused chain (GPU box): python tools/trace_chain.py [sdfq|geom|color]"""
-import copy, ctypes as C, os, sys, numpy as np, torch
+"""Pipeline trace of one CTA of a fused chain (GPU box): python tools/trace_chain.py [sdfq|geom|color]
+Rebuilds the library with -DES_TRACE (the trace hooks are compiled out of the product build) and restores it after."""
+import copy, ctypes as C, os, subprocess, sys, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+if os.environ.get("ES_TRACE_CHILD") != "1":
+    env = dict(os.environ, ES_NVCC_FLAGS="-DES_TRACE", ES_TRACE_CHILD="1")
+    subprocess.check_call([sys.executable, "-m", "endosurf_b200.build", "--force"], cwd=ROOT, env=env, stdout=subprocess.DEVNULL)
+    try:
+        subprocess.check_call([sys.executable] + sys.argv, cwd=ROOT, env=env)
+    finally:
+        subprocess.check_call([sys.executable, "-m", "endosurf_b200.build", "--force"], cwd=ROOT, stdout=subprocess.DEVNULL)
+    sys.exit(0)
+import torch
 from conftest import load_cfg, load_ckpt
 from endosurf_b200 import EndoSurfRenderer, _lib
 which = sys.argv[1] if len(sys.argv) > 1 else "geom"
