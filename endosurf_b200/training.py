@@ -68,6 +68,12 @@ def points_from_rows(r: torch.Tensor) -> torch.Tensor:
     return r.reshape(rows // 128, 4, 4, 8, -1).permute(0, 1, 3, 2, 4).reshape(rows // 4, 4, -1)
 
 
+def stream_rows(r: torch.Tensor, s: int) -> torch.Tensor:
+    """Rows of stream s (0 = primal) of a [rows, k] geometry plane in point order -> [rows / 4, k] (copies a quarter)."""
+    rows = r.shape[0]
+    return r.view(rows // 128, 4, 4, 8, -1)[:, :, s].reshape(rows // 4, -1)
+
+
 _MM_OUT_DTYPE_OK = None
 # fp16 hi/lo terms of the weight-gradient GEMMs.  1 = zbar_hi^T @ stash_hi with fp32 accumulation: the rounding of the
 # individual products (2^-11) averages out over the >= 10^5 rows of a batch - measured on a 1024-ray batch against
@@ -345,8 +351,8 @@ class PointFieldFn(torch.autograd.Function):
         rr_hi, rr_lo = padded_planes(r_rows.reshape(n, 4, 1), g_rows)
         sl = sdf_off + L - 1
         g_row0 = tn_planes(rr_hi, rr_lo, gs_hi[sl], gs_lo[sl])[:1]        # [1,256]
-        h8p_hi = points_from_rows(gs_hi[sl])[:n, 0].contiguous()          # primal rows of the output layer's input
-        h8p_lo = points_from_rows(gs_lo[sl])[:n, 0].contiguous()
+        h8p_hi = stream_rows(gs_hi[sl], 0)[:n]                            # primal rows of the output layer's input
+        h8p_lo = stream_rows(gs_lo[sl], 0)[:n]
         fb_hi, fb_lo = split16(feat_bar)
         gw[1][L - 1] = torch.cat([g_row0, tn_planes(fb_hi, fb_lo, h8p_hi, h8p_lo)], 0)
         gb[1][L - 1] = torch.cat([sdf_bar.sum(0), feat_bar.sum(0)], 0)
