@@ -215,6 +215,20 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+__device__ __forceinline__ void umma_commit_sa(uint32_t bar_sa) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_sa) : "memory");
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ fp16 hi/lo split
 // x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi) (round-to-nearest-even): 22 mantissa bits, i.e. a relative
 // representation error of 2^-22, 16x tighter than a bf16 pair for the same three MMAs (hi*hi + hi*lo + lo*hi).

@@ -1032,13 +1032,15 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           ++wc;
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ============================================================== MMA issuer
-      // One thread feeds the tensor pipe; it must stay well ahead of the 128 cycles an M128 N256 K16 UMMA takes, so
-      // the loop body is a handful of 64-bit adds on precomputed descriptors (a naive loop that rebuilt the
-      // descriptors cost ~285 cycles per MMA and capped the tensor pipe at 31 %, profiles/r1_ncu_summary_v1.txt).
+      // The tensor pipe retires one M128 N256 K16 UMMA every 128 cycles, and this warp shares its SM sub-partition's
+      // issue slots with four busy epilogue warps, so the loop must cost only a few instructions per MMA
+      // (tools/mma_noise.py: an 18-instruction issue loop falls from 181 to 260 cycles/MMA under epilogue-like load).
+      // The WHOLE warp walks the loop, so every value is warp-uniform and lives in uniform registers - no
+      // elect/R2UR broadcast sequence in front of each UTCHMMA - and one elected lane issues.  Ring positions are
+      // wrapped counters, not divisions.
       constexpr uint32_t idesc = make_idesc_f16(TILE_ROWS, HID);
-      uint32_t wc = 0, ac = 0, g = 0;
 #ifdef ES_TRACE
       unsigned tcount = 0;
 #endif
@@ -1050,6 +1052,10 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       constexpr uint64_t W_KS = (2 * B_LBO) >> 4;
       const bool three = prog.n_terms == 3;
       const bool do_mma = !ES_FLAG(io, 4);
+      const bool leader = elect_one_sync();
+      uint32_t st = 0, w_par = 0;      // weight ring stage and its phase parity
+      uint32_t slot = 0, a_par = 0;    // A ring slot and its phase parity
+      uint32_t g = 0;                  // global layer counter (accumulator buffer g & 1)
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < prog.n_layers; ++l, ++g) {
           const LayerProg& L = prog.layer[l];
@@ -1059,50 +1065,53 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           tc_fence_after();
           TRACE_MMA(1000 + l);  // MMA: accumulator free, layer l starts
           uint32_t accum = 0;
-          for (int ck = 0; ck < n_chunks; ++ck, ++ac) {
-            const uint32_t slot = ac % NSLOT;
+          for (int ck = 0; ck < n_chunks; ++ck) {
             const int nsub = L.nsub[ck];
-            mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, (ac / NSLOT) & 1, err, 310);
+            mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 310);
             tc_fence_after();
             TRACE_MMA(2000 + l * 16 + ck);  // MMA: chunk ck of layer l available
             uint64_t a_hi = a_desc0 + static_cast<uint64_t>(slot * (SLOT_BYTES >> 4));
             for (int sb = 0; sb < nsub; ++sb, a_hi += A_SB) {
               // ---- hi weight unit: A_hi*B_hi and A_lo*B_hi
               {
-                const uint32_t st = wc % NSTAGE;
-                mbar_wait_sa(sm + BAR_W_FULL + 8 * st, (wc / NSTAGE) & 1, err, 320);
+                mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 320);
                 tc_fence_after();
                 const uint64_t wd = w_desc0 + static_cast<uint64_t>(st * (UNIT_BYTES >> 4));
-                if (do_mma) {
-                  umma_f16_ss(d_tmem, a_hi, wd, idesc, accum);
-                  if (three) umma_f16_ss(d_tmem, a_hi + A_LO, wd, idesc, 1);
-                  umma_f16_ss(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
-                  if (three) umma_f16_ss(d_tmem, a_hi + A_LO + A_KS, wd + W_KS, idesc, 1);
+                if (leader) {
+                  if (do_mma) {
+                    umma_f16_ss(d_tmem, a_hi, wd, idesc, accum);
+                    if (three) umma_f16_ss(d_tmem, a_hi + A_LO, wd, idesc, 1);
+                    umma_f16_ss(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
+                    if (three) umma_f16_ss(d_tmem, a_hi + A_LO + A_KS, wd + W_KS, idesc, 1);
+                  }
+                  umma_commit_sa(sm + BAR_W_EMPTY + 8 * st);
                 }
                 accum = 1;
-                umma_commit(reinterpret_cast<uint64_t*>(smem + BAR_W_EMPTY) + st);
-                ++wc;
+                if (++st == NSTAGE) { st = 0; w_par ^= 1; }
               }
               // ---- lo weight unit: A_hi*B_lo
               if (three) {
-                const uint32_t st = wc % NSTAGE;
-                mbar_wait_sa(sm + BAR_W_FULL + 8 * st, (wc / NSTAGE) & 1, err, 321);
+                mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 321);
                 tc_fence_after();
                 const uint64_t wd = w_desc0 + static_cast<uint64_t>(st * (UNIT_BYTES >> 4));
-                if (do_mma) {
-                  umma_f16_ss(d_tmem, a_hi, wd, idesc, 1);
-                  umma_f16_ss(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
+                if (leader) {
+                  if (do_mma) {
+                    umma_f16_ss(d_tmem, a_hi, wd, idesc, 1);
+                    umma_f16_ss(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
+                  }
+                  umma_commit_sa(sm + BAR_W_EMPTY + 8 * st);
                 }
-                umma_commit(reinterpret_cast<uint64_t*>(smem + BAR_W_EMPTY) + st);
-                ++wc;
+                if (++st == NSTAGE) { st = 0; w_par ^= 1; }
               }
             }
-            umma_commit(reinterpret_cast<uint64_t*>(smem + BAR_A_EMPTY) + slot);
+            if (leader) umma_commit_sa(sm + BAR_A_EMPTY + 8 * slot);
+            if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
           }
-          umma_commit(reinterpret_cast<uint64_t*>(smem + BAR_D_FULL) + (g & 1));
+          if (leader) umma_commit_sa(sm + BAR_D_FULL + 8 * (g & 1));
           TRACE_MMA(3000 + l);  // MMA: all MMAs of layer l issued
         }
       }
+      __syncwarp();
     }
   } else {
     // ============================================================== epilogue warps
