@@ -560,19 +560,20 @@ class EndoSurfRenderer(nn.Module):
         self._sync_weights()
         lib, ctx = _lib.load(), self._context()
         x = x.detach().reshape(-1, 3).contiguous().float()
-        d = d.detach().reshape(-1, 3).contiguous().float()
+        d = d.detach().reshape(-1, 3).contiguous().float() if d is not None else None  # None: geometry only, no rgb
         n = x.shape[0]
         t = t.detach().reshape(-1).contiguous().float()
         t_div = 1 if t.numel() == n else n
         dev = x.device
         o = dict(x_c=torch.empty(n, 3, device=dev), jac=torch.empty(n, 3, 3, device=dev),
-                 sdf=torch.empty(n, 1, device=dev), g_c=torch.empty(n, 3, device=dev),
-                 rgb=torch.empty(n, 3, device=dev))
+                 sdf=torch.empty(n, 1, device=dev), g_c=torch.empty(n, 3, device=dev))
+        if d is not None:
+            o["rgb"] = torch.empty(n, 3, device=dev)
         if want_feat:
             o["feat"] = torch.empty(n, 256, device=dev)
         _lib.check(ctx, lib.es_point_forward(ctx, _ptr(x), _ptr(t), t_div, 1, _ptr(d), 1, 3, n, _ptr(o["x_c"]),
                                              _ptr(o["jac"]), _ptr(o["sdf"]), _ptr(o["g_c"]), _ptr(o.get("feat")),
-                                             _ptr(o["rgb"]), self._stream()), "es_point_forward")
+                                             _ptr(o.get("rgb")), self._stream()), "es_point_forward")
         o["g_o"] = torch.einsum("nij,ni->nj", o["jac"], o["g_c"])
         return o
 

@@ -19,7 +19,8 @@ cfg = load_cfg(); r = EndoSurfRenderer(cfg["render"], cfg["net"], device="cuda")
 n = 148 * 128 * 4
 x = torch.rand(n, 3, device="cuda") - 0.5; t = torch.rand(n, device="cuda"); d = torch.randn(n, 3, device="cuda")
 lib, ctx = _lib.load(), r._context()
-fn = (lambda: r.sdf_from_observed_space(x, t)) if which == "sdfq" else (lambda: r.point_forward(x, d, t))
+fn = {"sdfq": lambda: r.sdf_from_observed_space(x, t), "geom": lambda: r.point_forward(x, None, t),
+      "color": lambda: r.point_forward(x, d, t)}[which]  # "color": both chains run, the colour chain's trace is the one kept
 fn(); torch.cuda.synchronize()
 lib.es_debug_trace(ctx, None, 0)
 fn(); torch.cuda.synchronize()
