@@ -1044,12 +1044,15 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
 #ifdef ES_TRACE
       unsigned tcount = 0;
 #endif
-      const uint64_t a_desc0 = make_smem_desc(sm + SM_A_OFF, A_LBO, A_SBO);
-      const uint64_t w_desc0 = make_smem_desc(sm + SM_W_OFF, B_LBO, B_SBO);
-      constexpr uint64_t A_KS = (2 * A_LBO) >> 4;          // one K=16 step inside a slot plane
-      constexpr uint64_t A_LO = SLOT_HALF_BYTES >> 4;      // hi plane -> lo plane
-      constexpr uint64_t A_SB = (4 * A_LBO) >> 4;          // one 32-wide sub-block
-      constexpr uint64_t W_KS = (2 * B_LBO) >> 4;
+      // descriptors as low words (address field in 16-byte units + LBO); the high words are compile-time constants
+      constexpr uint32_t A_HI32 = smem_desc_hi(A_SBO), W_HI32 = smem_desc_hi(B_SBO);
+      const uint32_t a_desc0 = smem_desc_lo(sm + SM_A_OFF, A_LBO);
+      const uint32_t w_desc0 = smem_desc_lo(sm + SM_W_OFF, B_LBO);
+      constexpr uint32_t A_KS = (2 * A_LBO) >> 4;          // one K=16 step inside a slot plane
+      constexpr uint32_t A_LO = SLOT_HALF_BYTES >> 4;      // hi plane -> lo plane
+      constexpr uint32_t A_SB = (4 * A_LBO) >> 4;          // one 32-wide sub-block
+      constexpr uint32_t W_KS = (2 * B_LBO) >> 4;
+      static_assert(((SM_W_OFF + NSTAGE * UNIT_BYTES) >> 4) < 0x4000, "descriptor address field");
       const bool three = prog.n_terms == 3;
       const bool do_mma = !ES_FLAG(io, 4);
       const bool leader = elect_one_sync();
@@ -1070,19 +1073,19 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
             mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 310);
             tc_fence_after();
             TRACE_MMA(2000 + l * 16 + ck);  // MMA: chunk ck of layer l available
-            uint64_t a_hi = a_desc0 + static_cast<uint64_t>(slot * (SLOT_BYTES >> 4));
+            uint32_t a_hi = a_desc0 + slot * (SLOT_BYTES >> 4);
             for (int sb = 0; sb < nsub; ++sb, a_hi += A_SB) {
               // ---- hi weight unit: A_hi*B_hi and A_lo*B_hi
               {
                 mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 320);
                 tc_fence_after();
-                const uint64_t wd = w_desc0 + static_cast<uint64_t>(st * (UNIT_BYTES >> 4));
+                const uint32_t wd = w_desc0 + st * (UNIT_BYTES >> 4);
                 if (leader) {
                   if (do_mma) {
-                    umma_f16_ss(d_tmem, a_hi, wd, idesc, accum);
-                    if (three) umma_f16_ss(d_tmem, a_hi + A_LO, wd, idesc, 1);
-                    umma_f16_ss(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
-                    if (three) umma_f16_ss(d_tmem, a_hi + A_LO + A_KS, wd + W_KS, idesc, 1);
+                    umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi, wd, idesc, accum);
+                    if (three) umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi + A_LO, wd, idesc, 1);
+                    umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
+                    if (three) umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi + A_LO + A_KS, wd + W_KS, idesc, 1);
                   }
                   umma_commit_sa(sm + BAR_W_EMPTY + 8 * st);
                 }
@@ -1093,11 +1096,11 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
               if (three) {
                 mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 321);
                 tc_fence_after();
-                const uint64_t wd = w_desc0 + static_cast<uint64_t>(st * (UNIT_BYTES >> 4));
+                const uint32_t wd = w_desc0 + st * (UNIT_BYTES >> 4);
                 if (leader) {
                   if (do_mma) {
-                    umma_f16_ss(d_tmem, a_hi, wd, idesc, 1);
-                    umma_f16_ss(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
+                    umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi, wd, idesc, 1);
+                    umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
                   }
                   umma_commit_sa(sm + BAR_W_EMPTY + 8 * st);
                 }

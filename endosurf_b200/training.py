@@ -141,7 +141,7 @@ def rowsum_planes(hi, lo, sel16: torch.Tensor) -> torch.Tensor:
     h, l = hi.view(torch.float16), lo.view(torch.float16)
     if h.shape[0] >= FAST_MIN_ROWS and _MM_OUT_DTYPE_OK is not False:
         try:
-            return (_mm16(sel16, h) + _mm16(sel16, l))[0]
+            return (_mm16(sel16, h) + _mm16(sel16, l))[0] if WGRAD_TERMS >= 2 else _mm16(sel16, h)[0]
         except (TypeError, RuntimeError):
             pass
     return (sel16.float() @ (h.float() + l.float()))[0]
@@ -405,6 +405,23 @@ def effective_weights(model) -> List[torch.Tensor]:
     return out
 
 
+class _CumprodPos(torch.autograd.Function):
+    """torch.cumprod along the last dim for strictly positive inputs (here 1 - alpha + 1e-7 >= 1e-7).  Same forward
+    values; the backward is the closed form  d/dx_j = sum_{k>=j} g_k y_k / x_j  without torch's data-dependent
+    zero check (a host sync, which also makes the step impossible to capture in a CUDA graph)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = torch.cumprod(x, -1)
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        return torch.flip(torch.cumsum(torch.flip(g * y, (-1,)), -1), (-1,)) / x
+
+
 def composite(sdf, g_o, rgb, rays_d, pts, z_vals, sample_dist, inv_s, cos_ratio):
     """NeuS alpha compositing of render_core (endosurf.py:168-203) in differentiable PyTorch (training path only;
     inference uses the CUDA composite kernel).  sdf [R,M], g_o [R,M,3], rgb [R,M,3]."""
@@ -417,7 +434,7 @@ def composite(sdf, g_o, rgb, rays_d, pts, z_vals, sample_dist, inv_s, cos_ratio)
     next_cdf = torch.sigmoid((sdf + iter_cos * dists * 0.5) * inv_s)
     alpha = ((prev_cdf - next_cdf + 1e-6) / (prev_cdf + 1e-6)).clip(0.0, 1.0)
     ones = torch.ones(R, 1, device=z_vals.device)
-    weights = alpha * torch.cumprod(torch.cat([ones, 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    weights = alpha * _CumprodPos.apply(torch.cat([ones, 1.0 - alpha + 1e-7], -1))[:, :-1]
     relax = (torch.linalg.norm(pts, dim=-1) < 1.2).to(sdf.dtype).detach()
     g_err = (torch.linalg.norm(g_o, dim=-1) - 1.0) ** 2
     g_err = (relax * g_err).sum() / (relax.sum() + 1e-6)
@@ -429,3 +446,59 @@ def composite(sdf, g_o, rgb, rays_d, pts, z_vals, sample_dist, inv_s, cos_ratio)
         "weights": weights,
         "cdf": prev_cdf,
     }
+
+
+class GraphedTrainStep:
+    """Forward + loss + backward of one training step captured in a CUDA graph.
+
+    The eager step is ~2500 launches (fused chains, library GEMMs and many small PyTorch ops on [R,M] tensors); replaying
+    them as one graph removes the launch gaps and the Python/dispatcher time.  Weight packing runs inside the graph, so
+    a replay always uses the current parameters.  ``iter_step`` (the cosine-anneal ratio, a host scalar in the
+    reference too, endosurf.py:215-219) is fixed at capture time: re-capture when it changes (it is constant after
+    ``anneal_end``).  Ray / target tensors are copied into static buffers; gradients land in the parameters' ``.grad``.
+
+        step = GraphedTrainStep(renderer, loss_fn, rays, (color_gt, depth_gt), iter_step)
+        out, loss = step(rays, color_gt, depth_gt); optimizer.step()
+    """
+
+    def __init__(self, renderer, loss_fn, rays, targets, iter_step, warmup=2):
+        self.renderer, self.loss_fn, self.iter_step = renderer, loss_fn, iter_step
+        self.rays = rays.detach().clone()
+        self.targets = [t.detach().clone() for t in targets]
+        self.params = [p for p in renderer.parameters() if p.requires_grad]
+        renderer.profile(False)  # event records are not part of the graph
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up on a side stream: workspace growth, cuBLAS handles, autotuning
+            for _ in range(warmup):
+                self._zero()
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._zero()
+        renderer._packed_version = None  # the sampling chains' weight packing must be part of the graph
+        self.graph = torch.cuda.CUDAGraph()
+        # "thread_local": the backward runs on autograd's device thread, whose bookkeeping calls (allocator growth,
+        # cuBLAS workspace queries) must not invalidate the capture; everything it enqueues on the capture stream is
+        # still recorded (tests/test_gpu_training.py::test_graphed_train_step checks replay == eager).
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            out, loss = self._run()
+        self.out = {k: v.detach() for k, v in out.items()}
+        self.loss = loss.detach()
+
+    def _zero(self):
+        for p in self.params:
+            p.grad = None
+
+    def _run(self):
+        out = self.renderer(self.rays, iter_step=self.iter_step)
+        loss = self.loss_fn(out, *self.targets)
+        loss.backward()
+        return out, loss
+
+    def __call__(self, rays, *targets):
+        self.rays.copy_(rays, non_blocking=True)
+        for s, t in zip(self.targets, targets):
+            s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.out, self.loss

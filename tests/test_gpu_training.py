@@ -166,7 +166,43 @@ def test_plane_gemm_fast_paths():
     e = ((out.double() - ref).norm() / ref.norm()).item()
     assert e < 2e-5, f"planes_mm: rel err {e:.3e}"
     sel = (torch.rand(1, rows, generator=g) < 0.25).to(torch.float16).cuda()
-    out = T.rowsum_planes(ah, al, sel)
     ref = (sel.double() @ a64)[0]
-    e = ((out.double() - ref).norm() / ref.norm()).item()
-    assert e < 2e-5, f"rowsum_planes: rel err {e:.3e}"
+    try:
+        for terms, tol in ((3, 2e-5), (1, 1e-3)):
+            T.WGRAD_TERMS = terms
+            out = T.rowsum_planes(ah, al, sel)
+            e = ((out.double() - ref).norm() / ref.norm()).item()
+            assert e < tol, f"rowsum_planes terms={terms}: rel err {e:.3e}"
+    finally:
+        T.WGRAD_TERMS = old
+
+
+def test_graphed_train_step(cfg, ckpt):
+    """A CUDA-graph replay of forward + loss + backward gives the gradients of the eager step on NEW inputs."""
+    from oracle import endosurf_oracle as orc
+    from endosurf_b200.training import GraphedTrainStep
+    r, rc, nc = _renderer(cfg, ckpt, 16, 16)
+    target0 = torch.full((64, 3), 0.25, device="cuda")
+    target1 = torch.full((64, 3), 0.6, device="cuda")
+    rays0 = orc.synthetic_rays(64, frame=2, seed=4).cuda()
+    rays1 = orc.synthetic_rays(64, frame=5, seed=9).cuda()
+
+    def lossf(o, tgt):
+        return (o["color_map"] - tgt).abs().mean() + 0.1 * o["gradient_o_error"] + 0.05 * o["depth_map"].mean()
+
+    gstep = GraphedTrainStep(r, lossf, rays0, (target0,), iter_step=1000)
+    out, loss = gstep(rays1, target1)
+    torch.cuda.synchronize()
+    g_graph = {n: p.grad.detach().clone() for n, p in r.model.named_parameters() if p.grad is not None}
+    loss_graph, color_graph = loss.item(), out["color_map"].clone()
+    r.zero_grad()
+    o = r(rays1, iter_step=1000)
+    l = lossf(o, target1)
+    l.backward()
+    r.sync_check()
+    assert rel_err(color_graph, o["color_map"].detach()) < 1e-6
+    assert abs(loss_graph - l.item()) <= 1e-6 * abs(l.item())
+    assert set(g_graph) == {n for n, p in r.model.named_parameters() if p.grad is not None}
+    num = sum(((g_graph[n] - p.grad) ** 2).sum().item() for n, p in r.model.named_parameters() if p.grad is not None)
+    den = sum((p.grad ** 2).sum().item() for p in r.model.parameters() if p.grad is not None)
+    assert (num / den) ** 0.5 < 1e-5, f"graph replay gradients differ from eager: {(num / den) ** 0.5:.3e}"

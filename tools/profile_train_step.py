@@ -20,4 +20,8 @@ print("mm out_dtype fast path:", training._MM_OUT_DTYPE_OK)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=60, max_name_column_width=90))
+if len(sys.argv) > 2:  # per input shape
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof2:
+        step(); torch.cuda.synchronize()
+    print(prof2.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=50, max_name_column_width=40))
