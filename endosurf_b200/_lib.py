@@ -50,6 +50,7 @@ EXPORTS = {
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     "es_train_layout": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "es_set_plane_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "es_point_forward_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                          C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 11),
     "es_point_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 7),

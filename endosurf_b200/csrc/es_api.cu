@@ -63,6 +63,9 @@ struct es_ctx {
   uint8_t* rev_units[3] = {nullptr, nullptr, nullptr};
   int rev_layers[3] = {0, 0, 0};
   ChainProg prog_rev[3]{};
+  // training planes: 0 (default) = write / read only the fp16 lo planes the 1-term weight-gradient path needs
+  // (softplus gating, input-layer adjoints); 1 = every lo plane (3-term weight gradients)
+  int full_planes = 0;
   // optional per-kernel timing (es_profile_*)
   bool profiling = false;
   long long* trace_dev = nullptr;  // debug pipeline trace buffer (es_debug_trace)
@@ -522,9 +525,36 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
   return 0;
 }
 
-static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const ChainProg& prog, const ChainIO& io,
+// Which lo planes a training launch touches (see es_ctx::full_planes).  kind: 0 geometry forward, 1 colour forward,
+// 3 + net reverse chains.
+static void apply_plane_mode(const es_ctx* ctx, int kind, ChainProg& p) {
+  const bool full = ctx->full_planes != 0;
+  const int skip = ctx->cfg.skip_layer;
+  const int Ld = ctx->cfg.use_deform ? ctx->cfg.n_layers - 1 : 0;
+  if (kind == 0) {
+    for (int l = 0; l < p.n_layers; ++l) p.layer[l].stash_lo = (full || l >= Ld) ? 1 : 0;  // sdf slots gate softplus
+    p.tail_stash_lo = full;
+  } else if (kind == 1) {
+    for (int l = 0; l < p.n_layers; ++l) p.layer[l].stash_lo = full;
+    p.tail_stash_lo = full;
+  } else if (kind >= 3) {
+    const int net = kind - 3;
+    const bool softplus = net == ES_NET_SDF;
+    const bool input_adj = net != ES_NET_DEFORM;  // the adjoint of the network input is needed (zbar of layers 0, skip)
+    for (int l = 0; l < p.n_layers; ++l) {
+      p.layer[l].gate_lo = (full || softplus) ? 1 : 0;
+      p.layer[l].zbar_lo = (full || (input_adj && p.layer[l].zbar_slot == skip)) ? 1 : 0;
+    }
+    p.post_gate_lo = (full || softplus) ? 1 : 0;
+    p.post_zbar_lo = (full || input_adj) ? 1 : 0;
+  }
+}
+
+static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const ChainProg& prog_in, const ChainIO& io,
                        cudaStream_t stream, bool bwd = false) {
   es_ctx::Timed t{kind, io.n_points, nullptr, nullptr};
+  ChainProg prog = prog_in;
+  if (io.stash_hi) apply_plane_mode(ctx, kind, prog);
   ChainIO io2 = io;
   io2.trace = ctx->trace_dev;
   {
@@ -694,6 +724,12 @@ int es_point_backward(es_ctx* ctx, int net, int64_t n, const uint16_t* stash_hi,
   io.dir_div = 1;
   return timed_chain(ctx, 3 + net, tangent ? CHAIN_SDF : CHAIN_COLOR, tangent, ctx->prog_rev[net], io,
                      static_cast<cudaStream_t>(stream), true);
+}
+
+int es_set_plane_mode(es_ctx* ctx, int32_t full_planes) {
+  if (!ctx) return ES_E_BADARG;
+  ctx->full_planes = full_planes != 0;
+  return 0;
 }
 
 int es_up_sample(es_ctx* ctx, const float* rays, int64_t n_rays, const float* z, const float* sdf, int32_t n,

@@ -232,7 +232,8 @@ __device__ __forceinline__ void publish_chunk(Epi& c, uint32_t slot, int code) {
 // slot (sa = slot base + 2 part A_LBO + 16 row).  DUMP: the same halves to global planes (pointers at this row's
 // first column of the part; training stash / zbar).
 template <bool SLOT, bool DUMP>
-__device__ __forceinline__ void emit_row(uint32_t sa, const float (&v)[PCOLS], uint16_t* dhi, uint16_t* dlo) {
+__device__ __forceinline__ void emit_row(uint32_t sa, const float (&v)[PCOLS], uint16_t* dhi, uint16_t* dlo,
+                                         bool dump_lo = true) {
   static_for<0, PCOLS / 8>([&](auto gc) {
     constexpr int g = decltype(gc)::value;
     uint32_t hi[4], lo[4];
@@ -244,17 +245,17 @@ __device__ __forceinline__ void emit_row(uint32_t sa, const float (&v)[PCOLS], u
     }
     if constexpr (DUMP) {
       *reinterpret_cast<uint4*>(dhi + 8 * g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(dlo + 8 * g) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (dump_lo) *reinterpret_cast<uint4*>(dlo + 8 * g) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   });
 }
 
 // read PCOLS values back from fp16 hi/lo planes (value = hi + lo)
-__device__ __forceinline__ void load_planes(const uint16_t* phi, const uint16_t* plo, float (&h)[PCOLS]) {
+__device__ __forceinline__ void load_planes(const uint16_t* phi, const uint16_t* plo, float (&h)[PCOLS], bool use_lo) {
 #pragma unroll
   for (int g = 0; g < PCOLS / 8; ++g) {
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(phi + 8 * g));
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(plo + 8 * g));
+    const uint4 b = use_lo ? __ldg(reinterpret_cast<const uint4*>(plo + 8 * g)) : make_uint4(0u, 0u, 0u, 0u);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -355,9 +356,10 @@ __device__ __forceinline__ void load_raw(const Epi& c, int buf, int blk, float (
 //   softplus : sigma = 1 - exp(-100 h_primal)    (h = softplus(z)  =>  sigma(100 z) = 1 - exp(-100 h))
 //              tangent rows: zdotbar_j = sigma * u_j
 //              primal row  : zbar = sigma * u + 100 (1 - sigma) * sum_j hdot_j * u_j      (softplus'' = 100 s (1-s))
-__device__ __forceinline__ void bwd_gate_plain(const uint16_t* shi, const uint16_t* slo, int act, float (&u)[PCOLS]) {
+__device__ __forceinline__ void bwd_gate_plain(const uint16_t* shi, const uint16_t* slo, int act, bool use_lo,
+                                               float (&u)[PCOLS]) {
   float h[PCOLS];
-  load_planes(shi, slo, h);
+  load_planes(shi, slo, h, use_lo);
   if (act == ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < PCOLS; ++i) u[i] = h[i] > 0.f ? u[i] : 0.f;
@@ -391,7 +393,7 @@ __device__ __forceinline__ void dot_accum(const float (&v)[PCOLS], const float* 
 // st_hi / st_lo: training stash planes at this row's column 0, or null.
 template <int NOUT>
 static __device__ __noinline__ float4 tail_dot(Epi c, uint32_t g_layer, int act, int bias, const float* w_out,
-                                               uint16_t* st_hi, uint16_t* st_lo) {
+                                               uint16_t* st_hi, uint16_t* st_lo, bool st_lo_on) {
   wait_d_full(c, g_layer);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -399,7 +401,7 @@ static __device__ __noinline__ float4 tail_dot(Epi c, uint32_t g_layer, int act,
     float v[PCOLS];
     load_act_dyn(c, act, g_layer & 1, blk, bias, v);
     const int co = 64 * blk + PCOLS * c.part;
-    if (st_hi) emit_row<false, true>(0, v, st_hi + co, st_lo + co);
+    if (st_hi) emit_row<false, true>(0, v, st_hi + co, st_lo + co, st_lo_on);
     dot_accum<NOUT>(v, w_out + co, acc);
   }
   release_d(c, g_layer);
@@ -440,7 +442,7 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
 
       if (!BWD && L.pre_op == PRE_DEFORM_TAIL) {
         // deform output layer (3 x 256, fp32 FFMA) -> x_c = x + delta
-        float4 r = tail_dot<3>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, nullptr, nullptr);
+        float4 r = tail_dot<3>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, nullptr, nullptr, false);
         xc[0] += r.x + __ldg(prog.deform_out_b + 0);
         xc[1] += r.y + __ldg(prog.deform_out_b + 1);
         xc[2] += r.z + __ldg(prog.deform_out_b + 2);
@@ -477,9 +479,9 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
                      adj[2] * __ldg(prog.outer3_w + 2 * HID + col0 + i);
           }
           const size_t so = (static_cast<size_t>(L.stash_slot) * io.stash_rows + row_global) * HID + col0;
-          bwd_gate_plain(io.stash_hi + so, io.stash_lo + so, L.bwd_act, v);
+          bwd_gate_plain(io.stash_hi + so, io.stash_lo + so, L.bwd_act, L.gate_lo != 0, v);
           const size_t zo = (static_cast<size_t>(L.zbar_slot) * io.stash_rows + row_global) * HID + col0;
-          emit_row<true, true>(row_sa, v, io.zbar_hi + zo, io.zbar_lo + zo);
+          emit_row<true, true>(row_sa, v, io.zbar_hi + zo, io.zbar_lo + zo, L.zbar_lo != 0);
         } else if (src == SRC_PREV) {
           float v[PCOLS];
           if (!prev_waited) {
@@ -492,7 +494,7 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
           TRACE_EPI(7000 + l * 16 + ck);  // EPI: values ready (tmem + math done)
           if constexpr (STASH) {  // training: keep this layer's input for the reverse pass / weight gradients
             const size_t so = (static_cast<size_t>(l) * io.stash_rows + row_global) * HID + col0;
-            emit_row<true, true>(row_sa, v, io.stash_hi + so, io.stash_lo + so);
+            emit_row<true, true>(row_sa, v, io.stash_hi + so, io.stash_lo + so, L.stash_lo != 0);
           } else {
             emit_row<true, false>(row_sa, v, nullptr, nullptr);
           }
@@ -544,7 +546,7 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
     const int last = prog.n_layers - 1;
     const int act_last = prog.layer[last].act;
     if (!BWD && prog.post_op == POST_SDF_TAIL) {
-      float4 r = tail_dot<1>(c, c.g - 1, act_last, last, prog.sdf_out_w, nullptr, nullptr);
+      float4 r = tail_dot<1>(c, c.g - 1, act_last, last, prog.sdf_out_w, nullptr, nullptr, false);
       if (c.part == 0 && valid && io.out_sdf) io.out_sdf[pt] = r.x + __ldg(prog.sdf_out_b);
     } else if (BWD && prog.post_op == POST_BWD_DUMP) {
       wait_d_full(c, c.g - 1);
@@ -554,15 +556,15 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
         const int col0 = 64 * blk + PCOLS * c.part;
         load_raw(c, (c.g - 1) & 1, blk, v);
         const size_t so = (static_cast<size_t>(prog.post_stash_slot) * io.stash_rows + row_global) * HID + col0;
-        bwd_gate_plain(io.stash_hi + so, io.stash_lo + so, prog.post_bwd_act, v);
+        bwd_gate_plain(io.stash_hi + so, io.stash_lo + so, prog.post_bwd_act, prog.post_gate_lo != 0, v);
         const size_t zo = (static_cast<size_t>(prog.post_zbar_slot) * io.stash_rows + row_global) * HID + col0;
-        emit_row<false, true>(0, v, io.zbar_hi + zo, io.zbar_lo + zo);
+        emit_row<false, true>(0, v, io.zbar_hi + zo, io.zbar_lo + zo, prog.post_zbar_lo != 0);
       }
       release_d(c, c.g - 1);
     } else if (!BWD && prog.post_op == POST_COLOR_TAIL) {
       uint16_t* sh = STASH ? io.stash_hi + (static_cast<size_t>(prog.n_layers) * io.stash_rows + row_global) * HID : nullptr;
       uint16_t* sl = STASH ? io.stash_lo + (static_cast<size_t>(prog.n_layers) * io.stash_rows + row_global) * HID : nullptr;
-      float4 r = tail_dot<3>(c, c.g - 1, act_last, last, prog.color_out_w, sh, sl);
+      float4 r = tail_dot<3>(c, c.g - 1, act_last, last, prog.color_out_w, sh, sl, prog.tail_stash_lo != 0);
       if (c.part == 0 && valid) {
         float o[3] = {r.x, r.y, r.z};
 #pragma unroll
@@ -627,7 +629,7 @@ __device__ __forceinline__ void act_frag_dyn(int act, uint32_t bias_sa, Frag& F)
 // split to fp16 hi/lo and store.  SLOT: sa = this thread's base inside an A ring slot (k-group 2 part, row 32Q + p,
 // byte 4q).  DUMP: dhi/dlo = global plane pointers at (row of stream 0, col(0)) (training stash / zbar).
 template <bool SLOT, bool DUMP>
-__device__ __forceinline__ void emit_frag(const Frag& F, uint32_t sa, uint16_t* dhi, uint16_t* dlo) {
+__device__ __forceinline__ void emit_frag(const Frag& F, uint32_t sa, uint16_t* dhi, uint16_t* dlo, bool dump_lo = true) {
   static_for<0, 4>([&](auto sc) {
     constexpr int s = decltype(sc)::value;
     static_for<0, 2>([&](auto jc) {
@@ -640,20 +642,20 @@ __device__ __forceinline__ void emit_frag(const Frag& F, uint32_t sa, uint16_t* 
       }
       if constexpr (DUMP) {
         *reinterpret_cast<uint32_t*>(dhi + s * 8 * HID + 8 * j) = hi;
-        *reinterpret_cast<uint32_t*>(dlo + s * 8 * HID + 8 * j) = lo;
+        if (dump_lo) *reinterpret_cast<uint32_t*>(dlo + s * 8 * HID + 8 * j) = lo;
       }
     });
   });
 }
 
 // fragment of fp16 hi/lo planes (value = hi + lo); pointers at (row of stream 0, col(0))
-__device__ __forceinline__ void load_planes_frag(const uint16_t* phi, const uint16_t* plo, Frag& H) {
+__device__ __forceinline__ void load_planes_frag(const uint16_t* phi, const uint16_t* plo, Frag& H, bool use_lo) {
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(phi + s * 8 * HID + 8 * j));
-      const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(plo + s * 8 * HID + 8 * j));
+      const uint32_t b = use_lo ? __ldg(reinterpret_cast<const uint32_t*>(plo + s * 8 * HID + 8 * j)) : 0u;
       const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&a));
       const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&b));
       H.f[s][2 * j] = fa.x + fb.x;
@@ -663,9 +665,9 @@ __device__ __forceinline__ void load_planes_frag(const uint16_t* phi, const uint
 }
 
 // activation backward on a fragment (see bwd_gate_plain for the formulas); everything is thread-local
-__device__ __forceinline__ void bwd_gate_frag(const uint16_t* shi, const uint16_t* slo, int act, Frag& U) {
+__device__ __forceinline__ void bwd_gate_frag(const uint16_t* shi, const uint16_t* slo, int act, bool use_lo, Frag& U) {
   Frag H;
-  load_planes_frag(shi, slo, H);
+  load_planes_frag(shi, slo, H, use_lo);
   if (act == ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -736,7 +738,7 @@ __device__ __forceinline__ void point_sum(const Epi& c, float (&v)[NV]) {
 // streams.  st_hi / st_lo: training stash planes at (row of stream 0, column 0), or null.  Out of line.
 template <int NOUT>
 static __device__ __noinline__ void tail_frag(Epi c, uint32_t g_layer, int act, int bias, const float* w_out,
-                                              uint16_t* st_hi, uint16_t* st_lo, float* out) {
+                                              uint16_t* st_hi, uint16_t* st_lo, bool st_lo_on, float* out) {
   wait_d_full(c, g_layer);
   float acc[4][NOUT];
 #pragma unroll
@@ -749,7 +751,7 @@ static __device__ __noinline__ void tail_frag(Epi c, uint32_t g_layer, int act, 
     Frag F;
     load_frag(c.tmem + (g_layer & 1) * HID + 64 * blk, F);
     act_frag_dyn(act, c.sm + SM_BIAS_OFF + (bias * HID + 64 * blk + colq) * 4, F);
-    if (st_hi) emit_frag<false, true>(F, 0, st_hi + 64 * blk + colq, st_lo + 64 * blk + colq);
+    if (st_hi) emit_frag<false, true>(F, 0, st_hi + 64 * blk + colq, st_lo + 64 * blk + colq, st_lo_on);
     dot_frag<NOUT>(F, w_out + 64 * blk + colq, acc);
   }
   release_d(c, g_layer);
@@ -800,7 +802,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
         uint16_t* sh = STASH ? io.stash_hi + (static_cast<size_t>(l) * io.stash_rows + row0) * HID : nullptr;
         uint16_t* sl = STASH ? io.stash_lo + (static_cast<size_t>(l) * io.stash_rows + row0) * HID : nullptr;
         float o[12];
-        tail_frag<3>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, sh, sl, o);
+        tail_frag<3>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, sh, sl, prog.tail_stash_lo != 0, o);
 #pragma unroll
         for (int i = 0; i < 3; ++i) xc[i] += o[i] + __ldg(prog.deform_out_b + i);
         if (writer && valid) {
@@ -840,7 +842,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
             TRACE_EPI(7000 + l * 16 + ck);  // EPI: values ready (tmem + math done)
             if constexpr (STASH) {  // training: keep this layer's input for the reverse pass / weight gradients
               const size_t so = (static_cast<size_t>(l) * io.stash_rows + row0) * HID + 64 * blk + colq;
-              emit_frag<true, true>(F, slot_sa + frag_off, io.stash_hi + so, io.stash_lo + so);
+              emit_frag<true, true>(F, slot_sa + frag_off, io.stash_hi + so, io.stash_lo + so, L.stash_lo != 0);
             } else {
               emit_frag<true, false>(F, slot_sa + frag_off, nullptr, nullptr);
             }
@@ -906,9 +908,9 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
               }
             }
             const size_t so = (static_cast<size_t>(L.stash_slot) * io.stash_rows + row0) * HID + 64 * blk + colq;
-            bwd_gate_frag(io.stash_hi + so, io.stash_lo + so, L.bwd_act, F);
+            bwd_gate_frag(io.stash_hi + so, io.stash_lo + so, L.bwd_act, L.gate_lo != 0, F);
             const size_t zo = (static_cast<size_t>(L.zbar_slot) * io.stash_rows + row0) * HID + 64 * blk + colq;
-            emit_frag<true, true>(F, slot_sa + frag_off, io.zbar_hi + zo, io.zbar_lo + zo);
+            emit_frag<true, true>(F, slot_sa + frag_off, io.zbar_hi + zo, io.zbar_lo + zo, L.zbar_lo != 0);
           }
         }
         publish_chunk(c, slot, l * 16 + ck);
@@ -932,7 +934,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
     const int last = prog.n_layers - 1;
     if (!BWD && prog.post_op == POST_SDF_TAIL) {
       float o[4];
-      tail_frag<1>(c, c.g - 1, prog.layer[last].act, last, prog.sdf_out_w, nullptr, nullptr, o);
+      tail_frag<1>(c, c.g - 1, prog.layer[last].act, last, prog.sdf_out_w, nullptr, nullptr, false, o);
       if (writer && valid) {
         if (q == 0) {
           if (io.out_sdf) io.out_sdf[pt] = o[0] + __ldg(prog.sdf_out_b);
@@ -947,9 +949,9 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
         Frag F;
         load_frag(c.tmem + ((c.g - 1) & 1) * HID + 64 * blk, F);
         const size_t so = (static_cast<size_t>(prog.post_stash_slot) * io.stash_rows + row0) * HID + 64 * blk + colq;
-        bwd_gate_frag(io.stash_hi + so, io.stash_lo + so, prog.post_bwd_act, F);
+        bwd_gate_frag(io.stash_hi + so, io.stash_lo + so, prog.post_bwd_act, prog.post_gate_lo != 0, F);
         const size_t zo = (static_cast<size_t>(prog.post_zbar_slot) * io.stash_rows + row0) * HID + 64 * blk + colq;
-        emit_frag<false, true>(F, 0, io.zbar_hi + zo, io.zbar_lo + zo);
+        emit_frag<false, true>(F, 0, io.zbar_hi + zo, io.zbar_lo + zo, prog.post_zbar_lo != 0);
       }
       release_d(c, c.g - 1);
     } else if (!BWD && prog.post_op == POST_FEAT_OUT) {

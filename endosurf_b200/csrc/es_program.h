@@ -61,6 +61,10 @@ struct LayerProg {
   uint8_t zbar_slot;   // where this layer's input (adjoint of a forward pre-activation) is dumped for the weight grads
   uint8_t bwd_act;     // activation being differentiated (ACT_RELU / ACT_SOFTPLUS100)
   uint8_t rank1;       // 1: add adj.w * sdf_out_w[col] to the incoming adjoint (sdf row of the output layer)
+  // which fp16 lo planes the training path touches (host: apply_plane_mode; 1 everywhere in full-plane mode)
+  uint8_t stash_lo;    // forward: also write the lo plane of this layer's stash slot
+  uint8_t zbar_lo;     // reverse: also write the lo plane of this layer's zbar slot
+  uint8_t gate_lo;     // reverse: read the lo plane of the stash slot that gates this layer (softplus needs the value)
 };
 
 // host helper: fill LayerProg::last_prev after the chunk list is complete
@@ -88,6 +92,8 @@ struct ChainProg {
   const float* outer3_w;      // reverse chains: [3][256] output-layer weights for SRC_BWD_OUTER3
   // POST_BWD_DUMP: last activation-backward of a reverse chain (its result feeds no MMA, only the weight grads)
   int32_t post_stash_slot, post_zbar_slot, post_bwd_act;
+  int32_t post_zbar_lo, post_gate_lo;  // lo-plane flags of the POST_BWD_DUMP step
+  int32_t tail_stash_lo;               // lo plane of the 3-wide output layers' input stash (deform / colour tails)
 };
 
 // ------------------------------------------------------------------------------------------------------------------

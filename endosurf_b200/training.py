@@ -113,6 +113,8 @@ def tn_planes(a_hi, a_lo, b_hi, b_lo) -> torch.Tensor:
             return out
         except (TypeError, RuntimeError):
             _MM_OUT_DTYPE_OK = False
+    if WGRAD_TERMS == 1:  # the lo planes may not have been written (es_set_plane_mode)
+        return ah.float().t() @ bh.float()
     return (ah.float() + al.float()).t() @ (bh.float() + bl.float())
 
 
@@ -144,6 +146,8 @@ def rowsum_planes(hi, lo, sel16: torch.Tensor) -> torch.Tensor:
             return (_mm16(sel16, h) + _mm16(sel16, l))[0] if WGRAD_TERMS >= 2 else _mm16(sel16, h)[0]
         except (TypeError, RuntimeError):
             pass
+    if WGRAD_TERMS == 1:
+        return (sel16.float() @ h.float())[0]
     return (sel16.float() @ (h.float() + l.float()))[0]
 
 
@@ -191,6 +195,8 @@ class PointFieldFn(torch.autograd.Function):
             bs[net] = [b.detach().contiguous() for b in wb[k + L:k + 2 * L]]
             k += 2 * L
         _upload(renderer, epoch, nets, ws, bs, L)
+        _lib.check(ectx, lib.es_set_plane_mode(ectx, int(WGRAD_TERMS != 1)), "es_set_plane_mode")
+        ctx.full_planes = WGRAD_TERMS != 1
         lay = (C.c_int64 * 6)()
         _lib.check(ectx, lib.es_train_layout(ectx, n, lay), "es_train_layout")
         g_rows, g_slots, c_rows, c_slots, z_slots, sdf_off = [int(v) for v in lay]
@@ -234,6 +240,9 @@ class PointFieldFn(torch.autograd.Function):
         skip = cfg.skip_layer
         # the context may have been re-packed by another forward since; make sure it holds THIS call's weights
         _upload(renderer, ctx.epoch, nets, ws, bs, L)
+        if not ctx.full_planes and WGRAD_TERMS != 1:
+            raise RuntimeError("WGRAD_TERMS changed between forward and backward: the lo planes were not written")
+        _lib.check(ectx, lib.es_set_plane_mode(ectx, int(ctx.full_planes)), "es_set_plane_mode")
 
         def zeros_like_or(tns, shape):
             return tns if tns is not None else torch.zeros(shape, device=dev)

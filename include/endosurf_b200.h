@@ -79,6 +79,10 @@ int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div,
  *   Planes are uint16 (fp16 bits) [slots][rows][256]; geometry rows are ordered point-major: row = 4*point + stream
  *   (stream 0 = primal, 1..3 = d/dx, d/dy, d/dz), colour rows = point.                                             */
 int es_train_layout(const es_ctx* ctx, int64_t n, int64_t* out6);
+/* Which fp16 lo planes the training launches write/read.  0 (default): only those the 1-term weight-gradient path
+ * needs - the sdf stash slots (softplus gating) and the zbar slots of the layers that read the network input;
+ * 1: every plane (needed when the caller forms 3-term weight gradients from hi and lo). */
+int es_set_plane_mode(es_ctx* ctx, int32_t full_planes);
 int es_point_forward_train(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
                            const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
                            float* sdf, float* g_c, float* feat, float* rgb, uint16_t* geom_stash_hi,
