@@ -196,6 +196,10 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel at this workload's size, from the
+# committed ncu --set full capture (profiles/r1_v2_ncu_summary.txt); None = not captured for that variant yet
+NCU_TRAFFIC_BYTES = {"forward": 11.487488e6 + 525.844480e6, "train": None}
+
 METRICS = {"train": "training rays/sec (512x512 frames, 64+64 samples)",
            "forward": "render_rays forward rays/sec (512x512 frames, 64+64 samples)"}
 METRIC = METRICS["train"]
@@ -388,7 +392,7 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "mlp_chain_kernel<CHAIN_SDF,TANGENT> (forward geometry chain: "
                                                       "deform+sdf MLPs with 3 forward-mode tangent rows per point)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": NCU_TRAFFIC_BYTES.get(args.mode),
                          "algorithmic_flops_per_launch": alg_flops_launch, "points_per_launch": pts_per_launch,
                          "ms_per_launch": ms_launch,
                          "note": "algorithmic = 2*(4D+2S) FLOP/point (SURVEY 8d); the kernel issues 3 fp16 MMAs per "

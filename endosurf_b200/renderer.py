@@ -346,7 +346,7 @@ class EndoSurfRenderer(nn.Module):
             dd = rays_d[r0:r1, None, :].expand(r1 - r0, M, 3).reshape(n, 3)
             tt = time[r0:r1, None].expand(r1 - r0, M).reshape(n, 1)
             sdf, g_c, jac, rgb = self.point_field(x, dd, tt, wb)
-            g_o = torch.einsum("nij,ni->nj", jac, g_c)  # = autograd normal in observed space
+            g_o = (jac * g_c[:, :, None]).sum(1)  # J^T g_c = autograd normal in observed space
             sdf_l.append(sdf.reshape(r1 - r0, M))
             go_l.append(g_o.reshape(r1 - r0, M, 3))
             rgb_l.append(rgb.reshape(r1 - r0, M, 3))
@@ -369,7 +369,7 @@ class EndoSurfRenderer(nn.Module):
         (get_sdf_from_observed_space + get_sdf_grad_from_observed_space, endosurf.py:570-601)."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
             sdf, g_c, jac, _ = self.point_field(pts, dirs, t)
-            return sdf, torch.einsum("nij,ni->nj", jac, g_c)
+            return sdf, (jac * g_c[:, :, None]).sum(1)
         o = self.point_forward(pts, dirs, t)
         return o["sdf"], o["g_o"]
 

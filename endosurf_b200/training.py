@@ -282,7 +282,7 @@ class PointFieldFn(torch.autograd.Function):
             return split16(buf)
 
         # ============================================================== colour network
-        d_c_u = torch.bmm(jac, d.unsqueeze(-1)).squeeze(-1)
+        d_c_u = (jac * d[:, None, :]).sum(-1)   # J d; elementwise: batched 3x3 GEMMs cost 0.6 ms each
         d_c = d_c_u / (torch.linalg.norm(d_c_u, dim=-1, keepdim=True) + 1e-10)
         inp_c = torch.cat([freq_enc(x_c, cfg.multires_color_pos), g_c, freq_enc(d_c, cfg.multires_color_dir), feat], -1)
         inp_hi, inp_lo = padded_planes(inp_c, c_rows)
@@ -318,7 +318,7 @@ class PointFieldFn(torch.autograd.Function):
         with torch.enable_grad():
             xc_r = x_c.detach().requires_grad_(True)
             j_r = jac.detach().requires_grad_(True)
-            u = torch.bmm(j_r, d.unsqueeze(-1)).squeeze(-1)
+            u = (j_r * d[:, None, :]).sum(-1)
             dcr = u / (torch.linalg.norm(u, dim=-1, keepdim=True) + 1e-10)
             obj = (freq_enc(xc_r, cfg.multires_color_pos) * ex_bar).sum() + \
                 (freq_enc(dcr, cfg.multires_color_dir) * ed_bar).sum()
