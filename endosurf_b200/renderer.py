@@ -275,7 +275,7 @@ class EndoSurfRenderer(nn.Module):
         return self._consts[key]
 
     # ------------------------------------------------------------------ differentiable (training) path
-    train_ray_chunk = 2048  # rays per autograd.Function call: bounds the activation stash (about 21 GiB per chunk)
+    train_ray_chunk = 4096  # rays per autograd.Function call: bounds the activation stash (about 30 GiB per chunk of 4096 x 128 points)
 
     def point_field(self, x, d, t, wb=None):
         """Differentiable EndoSurfNet.forward + gradient queries on explicit points:
