@@ -193,12 +193,13 @@ def run_reference(args):
                                    f"{torch.__version__} CPU fp32, {threads} threads"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel at this workload's size, from the
-# committed ncu --set full capture (profiles/r1_v2_ncu_summary.txt); None = not captured for that variant yet
-NCU_TRAFFIC_BYTES = {"forward": 11.487488e6 + 525.844480e6, "train": None}
+# committed ncu --set full captures (profiles/r1_v2_ncu_summary.txt; training: the stash-writing variant, 524288 points,
+# tools/ncu_one_kernel.sh -> profiles/r1_v2_ncu_stash_kernel.txt)
+NCU_TRAFFIC_BYTES = {"forward": 11.487488e6 + 525.844480e6, "train": 0.696432896e9 + 26.990113e9}
 
 METRICS = {"train": "training rays/sec (512x512 frames, 64+64 samples)",
            "forward": "render_rays forward rays/sec (512x512 frames, 64+64 samples)"}
@@ -410,12 +411,20 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.ref_rays} rays of the same workload ({args.mode}), oracle port "
                                               f"of the reference (PyTorch {torch.__version__} CPU fp32), {tt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = sys.stdout
+
+
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner on the first collective)
+    # are sent to stderr for the duration of the run
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

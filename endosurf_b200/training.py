@@ -30,22 +30,23 @@ SQRT2 = math.sqrt(2.0)
 
 # ------------------------------------------------------------------------------------------------ small torch helpers
 def freq_enc(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
-    """[x, sin(2^k x), cos(2^k x)]_k in the reference's column order (encoder.py:40-54)."""
-    out = [x]
-    for k in range(n_freqs):
-        f = float(2.0 ** k)
-        out += [torch.sin(x * f), torch.cos(x * f)]
-    return torch.cat(out, -1)
+    """[x, sin(2^k x), cos(2^k x)]_k in the reference's column order (encoder.py:40-54).  All frequencies in one
+    sin and one cos launch (x * 2^k is exact in fp32, so the values are those of the per-frequency loop)."""
+    if n_freqs == 0:
+        return x
+    f = torch.exp2(torch.arange(n_freqs, device=x.device, dtype=x.dtype))
+    arg = x[:, None, :] * f[None, :, None]                                  # [n, L, dim]
+    sc = torch.stack([torch.sin(arg), torch.cos(arg)], 2)                   # [n, L, 2, dim]
+    return torch.cat([x, sc.reshape(x.shape[0], -1)], -1)
 
 
 def freq_enc_tangent(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
     """d enc(x) / d x_j for j = 0..2  ->  [n, 3, 3(2L+1)] (what the kernels feed to the tangent rows)."""
     n, dim = x.shape
-    cols = [torch.ones_like(x)]
-    for k in range(n_freqs):
-        f = float(2.0 ** k)
-        cols += [f * torch.cos(x * f), -f * torch.sin(x * f)]
-    dfull = torch.cat(cols, -1)  # derivative of every column wrt its own component
+    f = torch.exp2(torch.arange(n_freqs, device=x.device, dtype=x.dtype))
+    arg = x[:, None, :] * f[None, :, None]
+    d = torch.stack([f[None, :, None] * torch.cos(arg), -f[None, :, None] * torch.sin(arg)], 2)  # [n, L, 2, dim]
+    dfull = torch.cat([torch.ones_like(x), d.reshape(n, -1)], -1)  # derivative of every column wrt its own component
     comp = (torch.arange(dfull.shape[1], device=x.device) % dim)
     sel = torch.stack([(comp == j) for j in range(dim)], 0).to(x.dtype)  # [3, width]
     return dfull[:, None, :] * sel[None, :, :]
