@@ -407,10 +407,11 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, tt = oracle_cpu_rays_per_s(args.ref_rays, 1, threads, args.mode)
+            v, tt = oracle_cpu_rays_per_s(args.ref_rays, 3, threads, args.mode)  # 1 warm-up + 3 timed passes, ~10 s
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.ref_rays} rays of the same workload ({args.mode}), oracle port "
-                                              f"of the reference (PyTorch {torch.__version__} CPU fp32), {tt:.1f} s"}
+                                              f"of the reference (PyTorch {torch.__version__} CPU fp32), median of 3 "
+                                              f"passes of {tt:.1f} s after one warm-up pass"}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -431,7 +432,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=4096, help="rays per step per GPU (BASELINE configs[1])")
-    ap.add_argument("--ref-rays", type=int, default=64, help="bounded CPU sample per step for the reference arm")
+    ap.add_argument("--ref-rays", type=int, default=512,
+                    help="bounded CPU sample per step for the reference arm / cpu_baseline (about 2.5 s of a 16-core host)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="train mode: replay forward+backward as one CUDA graph")
     ap.add_argument("--mode", default="train", choices=["train", "forward"],
