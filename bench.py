@@ -222,6 +222,10 @@ def workload_config(n_rays, note=None, mode="train"):
          "parallelism": ("rays sharded per rank; one NCCL all-reduce of the flat 1.65 M-float gradient bucket per step"
                          if mode == "train" else "rays sharded per rank, no data-path collective (forward)"),
          "l2_policy": "per-step working set (>= 1 GiB of per-point scratch) exceeds the 126 MB L2; ray batches rotate"}
+    if mode == "train":
+        c["precision"] = ("forward and activation-gradient chains: fp16 hi/lo x3 products (fp32 parity); weight/bias-gradient "
+                          "GEMMs: fp16 hi planes x1 with fp32 accumulation (training.WGRAD_TERMS = 1, measured 6.7e-5 "
+                          "whole-gradient deviation from exact fp32 products, DESIGN.md 6)")
     if note:
         c["note"] = note
     return c

@@ -52,10 +52,6 @@ def freq_enc_tangent(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
     return dfull[:, None, :] * sel[None, :, :]
 
 
-def planes_f32(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
-    return hi.view(torch.float16).float() + lo.view(torch.float16).float()
-
-
 def rows_from_points(v: torch.Tensor) -> torch.Tensor:
     """[p_g, 4, k] (point, stream) -> [4 p_g, k] in the geometry kernels' tile row order: a 128-row tile holds 32
     points; stream s of point (quadrant Q, p) is tile row 32 Q + 8 s + p (csrc/es_mlp.cu, tangent mode)."""
