@@ -1,3 +1,5 @@
+"""GPU box: which part of a training step can be captured in a CUDA graph (forward / point field / compositing / weight-norm fold /
+full colour loss), each variant in a fresh process.  Found torch.cumprod's backward (host sync) -> training._CumprodPos."""
 import copy, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) < 2:
