@@ -76,8 +76,11 @@ int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div,
  * pre-activation ("zbar") so that weight gradients are plain [256 x rows] x [rows x 256] GEMMs.
  *   es_train_layout: out6 = {geometry stash rows, geometry stash slots, colour stash rows, colour stash slots,
  *                            zbar slots per reverse chain, geometry slot offset of the sdf layers}.
- *   Planes are uint16 (fp16 bits) [slots][rows][256]; geometry rows are ordered point-major: row = 4*point + stream
- *   (stream 0 = primal, 1..3 = d/dx, d/dy, d/dz), colour rows = point.                                             */
+ *   Planes are uint16 (fp16 bits) [slots][rows][256].  Geometry rows follow the kernels' 128-row tiles of 32 points:
+ *   point = 32*tile + 8*Q + p (Q = 0..3, p = 0..7), stream s (0 = primal, 1..3 = d/dx, d/dy, d/dz) of that point is
+ *   row 128*tile + 32*Q + 8*s + p (one epilogue thread then owns the four streams of a point through the 16x256b
+ *   TMEM fragment loads; endosurf_b200/training.py rows_from_points / points_from_rows convert).  Colour rows =
+ *   point.  The adjoint input `adj` of es_point_backward stays indexed by (4*point + stream).                        */
 int es_train_layout(const es_ctx* ctx, int64_t n, int64_t* out6);
 /* Which fp16 lo planes the training launches write/read.  0 (default): only those the 1-term weight-gradient path
  * needs - the sdf stash slots (softplus gating) and the zbar slots of the layers that read the network input;
