@@ -33,7 +33,17 @@ class EsRenderOut(C.Structure):
 
 
 class EsProfile(C.Structure):
-    _fields_ = [("ms", C.c_double * 6), ("launches", C.c_int64 * 6), ("points", C.c_int64 * 6)]
+    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_int64 * 12), ("points", C.c_int64 * 12)]
+
+
+class EsTrainParams(C.Structure):
+    """es_train_params: [net] -> table of n_layers device pointers."""
+    _fields_ = [(n, C.POINTER(C.c_void_p) * 3) for n in ("v", "g", "grad_v", "grad_g", "grad_b")]
+
+
+class EsRenderGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "color_map", "depth_map", "gradients_o", "gradient_o_error", "weights", "cdf", "sdf", "sampled_color")]
 
 
 EXPORTS = {
@@ -42,6 +52,7 @@ EXPORTS = {
     "es_destroy": (None, [C.c_void_p]),
     "es_last_error": (C.c_char_p, [C.c_void_p]),
     "es_sync_check": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "es_poll_error": (C.c_int, [C.c_void_p, C.c_void_p]),
     "es_num_sms": (C.c_int, [C.c_void_p]),
     "es_load_network": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "es_sdf_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
@@ -49,11 +60,23 @@ EXPORTS = {
     "es_point_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
-    "es_train_layout": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "es_load_network_wn": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.c_void_p]),
     "es_set_plane_mode": (C.c_int, [C.c_void_p, C.c_int32]),
-    "es_point_forward_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
-                                         C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 11),
-    "es_point_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 7),
+    "es_train_stash_bytes": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "es_point_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                         C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 7),
+    "es_point_train_backward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64] +
+                                [C.c_void_p] * 9 + [C.POINTER(EsTrainParams), C.c_void_p]),
+    "es_render_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                          C.c_float] + [C.c_void_p] * 7 + [C.POINTER(EsRenderOut), C.c_void_p,
+                                                                           C.c_void_p]),
+    "es_render_train_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                           C.c_float] + [C.c_void_p] * 8 +
+                                 [C.POINTER(EsRenderGrads), C.POINTER(EsTrainParams), C.c_void_p, C.c_void_p]),
+    "es_debug_set": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "es_wgrad_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
     "es_up_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "es_render_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(EsRenderParams),

@@ -21,6 +21,7 @@ SOURCES = {
     "es_probe.cu": [],
     "es_mmabench.cu": [],
     "es_pack.cu": [],
+    "es_wgrad.cu": [],
     "es_rays.cu": ["-fmad=false"],
     "es_api.cu": [],
 }

@@ -55,6 +55,7 @@ struct es_ctx {
   float* small = nullptr;          // deform_out_w[768] deform_out_b[4] sdf_out_w[256] sdf_out_b[4] feat_out_b[256]
                                    // color_out_w[768] color_out_b[4]
   int* err_dev = nullptr;
+  int* err_host = nullptr;         // pinned mirror of err_dev, refreshed by es_poll_error
   // grow-only scratch
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
@@ -63,11 +64,41 @@ struct es_ctx {
   uint8_t* rev_units[3] = {nullptr, nullptr, nullptr};
   int rev_layers[3] = {0, 0, 0};
   ChainProg prog_rev[3]{};
-  // training planes: 0 (default) = write / read only the fp16 lo planes the 1-term weight-gradient path needs
-  // (softplus gating, input-layer adjoints); 1 = every lo plane (3-term weight gradients)
+  // input-adjoint launches: 0 = sdf enc rows (N 64), 1 = colour feature (N 256), 2 = colour enc/g_c/d_c (N 128)
+  uint8_t* inadj_units[3] = {nullptr, nullptr, nullptr};
+  int* inadj_cols_dev[3] = {nullptr, nullptr, nullptr};   // [2][n_mma] source columns of layer 0 / the skip layer
+  ChainProg prog_inadj[3]{};
+  // plane records of the training chains (chunks of 16 KiB per tile, es_program.h LayerProg::dump)
+  struct FwdLayout {
+    int n_dump = 0;
+    int in_idx[MAXL][MAXC];   // record index of input chunk ck of program layer l (duplicates resolved)
+    int tail = -1;            // first of the 4 dump-only chunks (deform tail / colour tail)
+  } lay_geom, lay_color;
+  // weight-norm fold targets: effective weights owned by the context (es_load_network_wn)
+  float* w_eff[3][16] = {};
+  // loss scales of the three reverse chains (device): amax bit patterns and the power-of-two scales
+  unsigned int* amax_dev = nullptr;   // [3]
+  float* scale_dev = nullptr;         // [3]
+  float* eik_den_dev = nullptr;       // [1] scratch
+  // cached weight-gradient work lists, keyed by (points, plane mode)
+  struct WgradPlan {
+    long long n = -1;
+    int full = 0;
+    WgradItem* items_dev = nullptr;
+    int n_items = 0;
+    std::vector<WgradJob> jobs;   // pointers patched per call
+    std::vector<int> job_net;     // ES_NET_* of every job
+    std::vector<int> job_layer;
+    int* colmaps_dev = nullptr;
+  };
+  std::vector<WgradPlan> wplans;
+  // training planes: 0 (default) = fp16 hi planes only (1-term weight gradients, hi-only activation gates) plus the
+  // lo halves the input-adjoint launches need; 1 = every lo plane (3-term weight gradients, exact gates)
   int full_planes = 0;
+  int wgrad_lbo = 0, wgrad_sbo = 0;   // debug override of the MN-major descriptor strides (0: built-in)
   // optional per-kernel timing (es_profile_*)
   bool profiling = false;
+  int debug_flags = 0;
   long long* trace_dev = nullptr;  // debug pipeline trace buffer (es_debug_trace)
   struct Timed {
     int kind;
@@ -256,6 +287,12 @@ void build_chain_programs(es_ctx* ctx) {
   const int Ls = static_cast<int>(S.progs.size());  // hidden + feat
   auto common = [&](ChainProg& p) {
     p.n_terms = cfg.precision_terms;
+    p.n_mma = HID;
+    p.unit_bytes = UNIT_BYTES;
+    p.pre_dump = p.pre_dump_lo = p.post_dump = p.post_dump_lo = NO_DUMP;
+    for (int l = 0; l < MAXL; ++l)
+      for (int k = 0; k < MAXC; ++k) p.layer[l].dump[k] = p.layer[l].dump_lo[k] = NO_DUMP;
+    for (int k = 0; k < MAXC; ++k) p.plane_lo[k] = NO_DUMP;
     p.deform_out_w = ctx->small + SM_DEFORM_W;
     p.deform_out_b = ctx->small + SM_DEFORM_B;
     p.sdf_out_w = ctx->small + SM_SDF_W;
@@ -279,12 +316,6 @@ void build_chain_programs(es_ctx* ctx) {
   g.bias = ctx->geom_bias;
   g.units_per_tile = static_cast<int>(ctx->geom_units_n);
   g.post_op = POST_FEAT_OUT;
-  ctx->prog_geom = g;
-  ChainProg q = g;
-  q.n_layers = n - 1;
-  q.units_per_tile = static_cast<int>(ctx->sdfq_units_n);
-  q.post_op = POST_SDF_TAIL;
-  ctx->prog_sdfq = q;
   ChainProg c{};
   common(c);
   c.n_layers = static_cast<int>(C.progs.size());
@@ -293,52 +324,137 @@ void build_chain_programs(es_ctx* ctx) {
   c.bias = ctx->color_bias;
   c.units_per_tile = static_cast<int>(ctx->color_units_n);
   c.post_op = POST_COLOR_TAIL;
+
+  // ---- plane records of the forward training chains: every input chunk of every layer is kept once (the skip
+  // layers re-read the network input, whose chunks are already in the record from layer 0), plus the inputs of the
+  // 3-wide output layers as 4 dump-only chunks
+  const int skip = cfg.skip_layer;
+  auto assign_forward = [&](ChainProg& p, es_ctx::FwdLayout& lay, int n_first /*layers of the first net*/) {
+    int idx = 0;
+    lay.tail = -1;
+    for (int l = 0; l < p.n_layers; ++l) {
+      LayerProg& G = p.layer[l];
+      if (G.pre_op == PRE_DEFORM_TAIL) {
+        lay.tail = idx;
+        p.pre_dump = static_cast<uint8_t>(idx);
+        idx += 4;
+      }
+      const int net_l = l < n_first ? l : l - n_first;   // layer index inside its network
+      const int l0 = l < n_first ? 0 : n_first;          // program index of that network's layer 0
+      int dup = 0;                                        // next input chunk of layer 0 this skip layer repeats
+      for (int k = 0; k < MAXC; ++k) G.dump[k] = G.dump_lo[k] = NO_DUMP;
+      for (int k = 0; k < G.n_chunks; ++k) {
+        const bool is_input = G.src[k] != SRC_PREV;
+        if (is_input && net_l == skip && net_l != 0) {
+          lay.in_idx[l][k] = lay.in_idx[l0][dup++];
+        } else {
+          lay.in_idx[l][k] = idx;
+          G.dump[k] = static_cast<uint8_t>(idx++);
+        }
+      }
+    }
+    if (p.post_op == POST_COLOR_TAIL) {
+      lay.tail = idx;
+      p.post_dump = static_cast<uint8_t>(idx);
+      idx += 4;
+    }
+    lay.n_dump = idx;
+    p.n_dump = idx;
+  };
+  assign_forward(g, ctx->lay_geom, Ld);
+  assign_forward(c, ctx->lay_color, c.n_layers);
+  ctx->prog_geom = g;
+  ChainProg q = g;
+  q.n_layers = n - 1;
+  q.units_per_tile = static_cast<int>(ctx->sdfq_units_n);
+  q.post_op = POST_SDF_TAIL;
+  ctx->prog_sdfq = q;
   ctx->prog_color = c;
 
-  // ---- reverse chains (es_point_backward): standard 4-chunk 256x256 layers on transposed weights
+  // ---- reverse chains (training backward): standard 4-chunk 256x256 layers on transposed weights.  The layer that
+  // carries W_m^T takes zbar_m (adjoint of forward layer m's pre-activation) as its A operand: chunk ck of reverse
+  // layer r is record chunk 4 r + ck of the chain's zbar record, the POST_BWD_DUMP result (zbar_0) is 4 n .. 4 n + 3.
   const int L = cfg.n_layers;
-  const int LdS = cfg.use_deform ? L - 1 : 0;  // geometry-chain slot offset of the sdf layers
-  auto rev_layer = [&](LayerProg& G, uint8_t src, int stash_slot, int zbar_slot, uint8_t act, bool rank1) {
+  auto rev_layer = [&](LayerProg& G, uint8_t src, int gate_base, int r, uint8_t act, bool rank1) {
     std::memset(&G, 0, sizeof(G));
     G.n_chunks = 4;
+    for (int k = 0; k < MAXC; ++k) G.dump[k] = G.dump_lo[k] = NO_DUMP;
     for (int k = 0; k < 4; ++k) {
       G.src[k] = src;
       G.arg[k] = static_cast<uint8_t>(k);
       G.nsub[k] = 2;
+      G.dump[k] = static_cast<uint8_t>(4 * r + k);
     }
-    G.stash_slot = static_cast<uint8_t>(stash_slot);
-    G.zbar_slot = static_cast<uint8_t>(zbar_slot);
+    G.gate_base = static_cast<uint8_t>(gate_base);
     G.bwd_act = act;
     G.rank1 = rank1 ? 1 : 0;
     finish_layer(G);
   };
   for (int net = 0; net < 3; ++net) {
+    if (net == ES_NET_DEFORM && !cfg.use_deform) continue;
     ChainProg r{};
     common(r);
     r.bias = ctx->geom_bias;
     r.w_units = ctx->rev_units[net];
     r.post_op = POST_BWD_DUMP;
-    r.post_zbar_slot = 0;
-    int n = 0;
+    const es_ctx::FwdLayout& lay = net == ES_NET_COLOR ? ctx->lay_color : ctx->lay_geom;
+    const int l0 = net == ES_NET_SDF ? Ld : 0;  // program index of this network's layer 0 in its forward chain
+    // record index of the activations a_{m+1} = act(z_m) that gate zbar_m: the SRC_PREV chunks of forward layer m+1
+    auto gate_of = [&](int m) {
+      if (m + 1 == L - 1 && net != ES_NET_SDF) return lay.tail;  // input of the 3-wide output layer
+      return lay.in_idx[l0 + m + 1][0];
+    };
+    int nr = 0;
     if (net == ES_NET_SDF) {
-      rev_layer(r.layer[n++], SRC_ADJ_FEAT, 0, 0, ACT_SOFTPLUS100, false);   // S_{L-1}^T (feature rows)
-      for (int m = L - 2; m >= 1; --m)                                        // S_m^T
-        rev_layer(r.layer[n++], SRC_BWD_PREV, LdS + m + 1, m, ACT_SOFTPLUS100, m == L - 2);
-      r.post_stash_slot = LdS + 1;
+      rev_layer(r.layer[nr], SRC_ADJ_FEAT, 0, nr, ACT_SOFTPLUS100, false);   // S_{L-1}^T (feature rows)
+      ++nr;
+      for (int m = L - 2; m >= 1; --m, ++nr)                                  // S_m^T
+        rev_layer(r.layer[nr], SRC_BWD_PREV, gate_of(m), nr, ACT_SOFTPLUS100, m == L - 2);
       r.post_bwd_act = ACT_SOFTPLUS100;
     } else {
-      const int tail_slot = net == ES_NET_DEFORM ? L - 1 : static_cast<int>(C.progs.size());
-      for (int m = L - 2; m >= 1; --m)
-        rev_layer(r.layer[n++], m == L - 2 ? SRC_BWD_OUTER3 : SRC_BWD_PREV, m == L - 2 ? tail_slot : m + 1, m,
-                  ACT_RELU, false);
-      r.post_stash_slot = 1;
+      for (int m = L - 2; m >= 1; --m, ++nr)
+        rev_layer(r.layer[nr], m == L - 2 ? SRC_BWD_OUTER3 : SRC_BWD_PREV, gate_of(m), nr, ACT_RELU, false);
       r.post_bwd_act = ACT_RELU;
       r.outer3_w = net == ES_NET_DEFORM ? ctx->small + SM_DEFORM_W : ctx->small + SM_COLOR_W;
     }
-    r.n_layers = n;
-    r.units_per_tile = n * 16;
-    ctx->rev_layers[net] = n;
+    r.post_gate_base = gate_of(0);
+    r.post_dump = static_cast<uint8_t>(4 * nr);
+    r.n_layers = nr;
+    r.n_dump = 4 * (nr + 1);
+    r.n_gate = lay.n_dump;
+    r.units_per_tile = nr * 16;
+    ctx->rev_layers[net] = nr;
     ctx->prog_rev[net] = r;
+  }
+
+  // ---- input-adjoint launches: ONE MMA layer, K = 512 = [zbar_0 | zbar_skip] reloaded from the zbar record,
+  // B = the input columns of W_0 and W_skip / sqrt 2 (es_load_network packs them)
+  for (int k = 0; k < 3; ++k) {
+    const int net = k == 0 ? ES_NET_SDF : ES_NET_COLOR;
+    ChainProg r{};
+    common(r);
+    r.bias = ctx->geom_bias;
+    r.w_units = ctx->inadj_units[k];
+    r.n_mma = k == 0 ? 64 : (k == 1 ? 256 : 128);
+    r.unit_bytes = r.n_mma * SUB_K * 2;
+    r.post_op = k == 0 ? POST_INADJ_SDF : (k == 1 ? POST_FEAT_BAR : POST_INADJ_COLOR);
+    const int nr = ctx->rev_layers[net];
+    const int r_skip = (net == ES_NET_SDF ? 1 : 0) + (L - 2 - skip);  // reverse layer whose input is zbar_skip
+    LayerProg& G = r.layer[0];
+    std::memset(&G, 0, sizeof(G));
+    for (int j = 0; j < MAXC; ++j) G.dump[j] = G.dump_lo[j] = NO_DUMP;
+    const bool has_skip = skip > 0 && skip < L - 1;
+    G.n_chunks = has_skip ? 8 : 4;
+    for (int j = 0; j < G.n_chunks; ++j) {
+      G.src[j] = SRC_PLANE;
+      G.nsub[j] = 2;
+      G.arg[j] = static_cast<uint8_t>(j < 4 ? 4 * nr + j : 4 * r_skip + (j - 4));
+    }
+    finish_layer(G);
+    r.n_layers = 1;
+    r.n_plane = 4 * (nr + 1);
+    r.units_per_tile = G.n_chunks * 4;
+    ctx->prog_inadj[k] = r;
   }
 }
 
@@ -358,7 +474,7 @@ int es_create(es_ctx** out, const es_net_config* cfg) {
     return ES_E_UNSUPPORTED;
   };
   if (c.hidden_dim != HID) return bad("hidden_dim must be 256");
-  if (c.n_layers < 3 || 2 * (c.n_layers - 1) + 1 > MAXL) return bad("n_layers out of range (3..10)");
+  if (c.n_layers < 3 || 2 * (c.n_layers - 1) + 1 > MAXL || c.n_layers > 16) return bad("n_layers out of range (3..10)");
   if (c.skip_layer == 0 || c.skip_layer >= c.n_layers - 1) return bad("skip_layer must be in [1, n_layers-2] or -1");
   if (c.multires_deform_pos != 6 || c.multires_deform_time != 6 || c.multires_sdf_pos != 6 ||
       c.multires_color_pos != 10 || c.multires_color_dir != 4)
@@ -416,6 +532,34 @@ int es_create(es_ctx** out, const es_net_config* cfg) {
     const int nl = net == ES_NET_SDF ? c.n_layers - 1 : c.n_layers - 2;
     CUC(cudaMalloc(&ctx->rev_units[net], static_cast<size_t>(nl) * 16 * UNIT_BYTES));
   }
+  for (int k = 0; k < 3; ++k) {
+    const int n_mma = k == 0 ? 64 : (k == 1 ? 256 : 128);
+    CUC(cudaMalloc(&ctx->inadj_units[k], static_cast<size_t>(32) * n_mma * SUB_K * 2));
+    CUC(cudaMemset(ctx->inadj_units[k], 0, static_cast<size_t>(32) * n_mma * SUB_K * 2));
+    // source columns (reference layout of the layer's input) of the N rows of the operand, layer 0 then skip layer
+    const int net = k == 0 ? ES_NET_SDF : ES_NET_COLOR;
+    const NetPlan& P = ctx->plan[net];
+    const int nx_c = 3 + 6 * c.multires_color_pos, nd_c = 3 + 6 * c.multires_color_dir;
+    std::vector<int> cols(2 * n_mma, -1);
+    for (int n = 0; n < n_mma; ++n) {
+      int rc = -1;
+      if (k == 0) rc = ref_column(c, net, chunk_feat(SRC_ENC_SDF, n));
+      else if (k == 1) rc = nx_c + 3 + nd_c + n;
+      else if (n < 64) rc = ref_column(c, net, chunk_feat(SRC_COLOR_A, n));
+      else if (n < 96) rc = ref_column(c, net, chunk_feat(SRC_COLOR_B, n - 64));
+      cols[n] = rc;
+      cols[n_mma + n] = rc < 0 ? -1 : P.out_dims[0] + rc;  // skip layer input = cat(h[256], network input)
+    }
+    CUC(cudaMalloc(&ctx->inadj_cols_dev[k], cols.size() * sizeof(int)));
+    CUC(cudaMemcpy(ctx->inadj_cols_dev[k], cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  for (int net = 0; net < 3; ++net)
+    for (int l = 0; l < c.n_layers; ++l)
+      CUC(cudaMalloc(&ctx->w_eff[net][l],
+                     static_cast<size_t>(ctx->plan[net].out_dims[l]) * ctx->plan[net].in_dims[l] * sizeof(float)));
+  CUC(cudaMalloc(&ctx->amax_dev, 4 * sizeof(unsigned int)));
+  CUC(cudaMalloc(&ctx->scale_dev, 4 * sizeof(float)));
+  CUC(cudaMalloc(&ctx->eik_den_dev, sizeof(float)));
   CUC(cudaMalloc(&ctx->err_dev, sizeof(int)));
   CUC(cudaMemset(ctx->geom_bias, 0, static_cast<size_t>(Ld + Ls) * HID * sizeof(float)));
   CUC(cudaMemset(ctx->color_bias, 0, C.packs.size() * HID * sizeof(float)));
@@ -442,7 +586,21 @@ void es_destroy(es_ctx* ctx) {
   cudaFree(ctx->color_bias);
   cudaFree(ctx->small);
   cudaFree(ctx->err_dev);
+  if (ctx->err_host) cudaFreeHost(ctx->err_host);
   for (int net = 0; net < 3; ++net) cudaFree(ctx->rev_units[net]);
+  for (int k = 0; k < 3; ++k) {
+    cudaFree(ctx->inadj_units[k]);
+    cudaFree(ctx->inadj_cols_dev[k]);
+  }
+  for (int net = 0; net < 3; ++net)
+    for (int l = 0; l < 16; ++l) cudaFree(ctx->w_eff[net][l]);
+  cudaFree(ctx->amax_dev);
+  cudaFree(ctx->scale_dev);
+  cudaFree(ctx->eik_den_dev);
+  for (auto& wp : ctx->wplans) {
+    cudaFree(wp.items_dev);
+    cudaFree(wp.colmaps_dev);
+  }
   cudaFree(ctx->ws);
   for (int net = 0; net < 3; ++net)
     for (auto& k : ctx->plan[net].packs) cudaFree(k.colmap_dev);
@@ -462,6 +620,24 @@ int es_sync_check(es_ctx* ctx, void* stream) {
     CU(cudaMemset(ctx->err_dev, 0, sizeof(int)));
     return fail(ctx, ES_E_DEVICE, "device-side barrier watchdog tripped, site code " + std::to_string(h));
   }
+  return 0;
+}
+
+int es_poll_error(es_ctx* ctx, void* stream) {
+  if (!ctx) return ES_E_BADARG;
+  if (!ctx->err_host) {
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->err_host), sizeof(int), cudaHostAllocDefault));
+    *ctx->err_host = 0;
+  }
+  // the value an EARLIER poll's copy delivered (never blocks; a tripped watchdog surfaces one call later at most)
+  const int h = *reinterpret_cast<volatile int*>(ctx->err_host);
+  if (h != 0) {
+    *ctx->err_host = 0;
+    CU(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int), static_cast<cudaStream_t>(stream)));
+    return fail(ctx, ES_E_DEVICE, "device-side barrier watchdog tripped, site code " + std::to_string(h));
+  }
+  CU(cudaMemcpyAsync(ctx->err_host, ctx->err_dev, sizeof(int), cudaMemcpyDeviceToHost,
+                     static_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -521,58 +697,144 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
       ++ctx->launches;
     }
   }
+  // operands of the input-adjoint launches: the network-input columns of W_0 and of W_skip / sqrt 2
+  if (net != ES_NET_DEFORM) {
+    const float inv_sqrt2 = static_cast<float>(1.0 / std::sqrt(2.0));
+    const int skip = ctx->cfg.skip_layer;
+    for (int k = (net == ES_NET_SDF ? 0 : 1); k <= (net == ES_NET_SDF ? 0 : 2); ++k) {
+      const int n_mma = ctx->prog_inadj[k].n_mma;
+      const size_t ub = static_cast<size_t>(n_mma) * SUB_K * 2;
+      CU(launch_pack_inadj(w[0], P.out_dims[0], P.in_dims[0], ctx->inadj_cols_dev[k], n_mma, 1.f,
+                           ctx->inadj_units[k], stream));
+      ++ctx->launches;
+      if (skip > 0 && skip < L - 1) {
+        CU(launch_pack_inadj(w[skip], P.out_dims[skip], P.in_dims[skip], ctx->inadj_cols_dev[k] + n_mma, n_mma,
+                             inv_sqrt2, ctx->inadj_units[k] + 16 * ub, stream));
+        ++ctx->launches;
+      }
+    }
+  }
   ctx->loaded[net] = true;
   return 0;
 }
 
-// Which lo planes a training launch touches (see es_ctx::full_planes).  kind: 0 geometry forward, 1 colour forward,
-// 3 + net reverse chains.
-static void apply_plane_mode(const es_ctx* ctx, int kind, ChainProg& p) {
+int es_load_network_wn(es_ctx* ctx, int net, const float* const* v, const float* const* g, const float* const* b,
+                       void* stream_) {
+  if (!ctx || !v || !g || !b || net < 0 || net > 2) return ES_E_BADARG;
+  if (net == ES_NET_DEFORM && !ctx->cfg.use_deform) return fail(ctx, ES_E_BADARG, "context built with use_deform=0");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const NetPlan& P = ctx->plan[net];
+  const int L = ctx->cfg.n_layers;
+  WnLayers tab{};
+  int max_rows = 0;
+  const float* w[16];
+  for (int l = 0; l < L; ++l) {
+    if (!v[l] || !g[l] || !b[l]) return fail(ctx, ES_E_BADARG, "null layer pointer");
+    WnLayer& W = tab.l[l];
+    W.v = v[l];
+    W.g = g[l];
+    W.w_eff = ctx->w_eff[net][l];
+    W.n_out = P.out_dims[l];
+    W.n_in = P.in_dims[l];
+    max_rows = std::max(max_rows, W.n_out);
+    w[l] = ctx->w_eff[net][l];
+  }
+  tab.n = L;
+  CU(launch_wn_fold(tab, max_rows, stream));
+  ++ctx->launches;
+  return es_load_network(ctx, net, w, b, stream_);
+}
+
+// profile slots (es_profile)
+enum { K_GEOM = 0, K_COLOR = 1, K_SDFQ = 2, K_REV_DEFORM = 3, K_REV_SDF = 4, K_REV_COLOR = 5, K_INADJ = 6, K_WGRAD = 7,
+       K_WREDUCE = 8, K_COMPOSITE = 9, K_SMALLM = 10, K_NKINDS = 12 };
+
+// reverse layer (of network `net`'s reverse chain) whose A operand is zbar of the skip layer
+static int rev_skip_layer(const es_ctx* ctx, int net) {
+  return (net == ES_NET_SDF ? 1 : 0) + (ctx->cfg.n_layers - 2 - ctx->cfg.skip_layer);
+}
+static bool has_skip(const es_ctx* ctx) {
+  return ctx->cfg.skip_layer > 0 && ctx->cfg.skip_layer < ctx->cfg.n_layers - 1;
+}
+
+// Which lo halves a training launch keeps / reads (see es_ctx::full_planes).  kind: K_GEOM / K_COLOR forward training
+// chains, K_REV_* reverse chains, K_INADJ + k input-adjoint launch k.
+static void apply_plane_mode(const es_ctx* ctx, int kind, int inadj_k, ChainProg& p) {
   const bool full = ctx->full_planes != 0;
-  const int skip = ctx->cfg.skip_layer;
-  const int Ld = ctx->cfg.use_deform ? ctx->cfg.n_layers - 1 : 0;
-  if (kind == 0) {
-    for (int l = 0; l < p.n_layers; ++l) p.layer[l].stash_lo = (full || l >= Ld) ? 1 : 0;  // sdf slots gate softplus
-    p.tail_stash_lo = full;
-  } else if (kind == 1) {
-    for (int l = 0; l < p.n_layers; ++l) p.layer[l].stash_lo = full;
-    p.tail_stash_lo = full;
-  } else if (kind >= 3) {
-    const int net = kind - 3;
-    const bool softplus = net == ES_NET_SDF;
-    const bool input_adj = net != ES_NET_DEFORM;  // the adjoint of the network input is needed (zbar of layers 0, skip)
-    for (int l = 0; l < p.n_layers; ++l) {
-      p.layer[l].gate_lo = (full || softplus) ? 1 : 0;
-      p.layer[l].zbar_lo = (full || (input_adj && p.layer[l].zbar_slot == skip)) ? 1 : 0;
+  if (kind == K_GEOM || kind == K_COLOR) {
+    if (full) {
+      for (int l = 0; l < p.n_layers; ++l)
+        for (int k = 0; k < p.layer[l].n_chunks; ++k) p.layer[l].dump_lo[k] = p.layer[l].dump[k];
+      p.pre_dump_lo = p.pre_dump;
+      p.post_dump_lo = p.post_dump;
+      p.n_dump_lo = p.n_dump;
+    } else {
+      p.n_dump_lo = 0;
     }
-    p.post_gate_lo = (full || softplus) ? 1 : 0;
-    p.post_zbar_lo = (full || input_adj) ? 1 : 0;
+  } else if (kind >= K_REV_DEFORM && kind <= K_REV_COLOR) {
+    const int net = kind - K_REV_DEFORM;
+    p.gate_use_lo = full ? 1 : 0;
+    if (full) {
+      for (int l = 0; l < p.n_layers; ++l)
+        for (int k = 0; k < p.layer[l].n_chunks; ++k) p.layer[l].dump_lo[k] = p.layer[l].dump[k];
+      p.post_dump_lo = p.post_dump;
+      p.n_dump_lo = p.n_dump;
+    } else if (net != ES_NET_DEFORM) {
+      // the input-adjoint launches need zbar_skip and zbar_0 to fp32 accuracy: compact lo record [skip x4 | zbar_0 x4]
+      int nlo = 0;
+      if (has_skip(ctx)) {
+        LayerProg& G = p.layer[rev_skip_layer(ctx, net)];
+        for (int k = 0; k < 4; ++k) G.dump_lo[k] = static_cast<uint8_t>(nlo++);
+      }
+      p.post_dump_lo = static_cast<uint8_t>(nlo);
+      nlo += 4;
+      p.n_dump_lo = nlo;
+    } else {
+      p.n_dump_lo = 0;
+    }
+  } else if (kind == K_INADJ) {
+    (void)inadj_k;
+    LayerProg& G = p.layer[0];
+    if (full) {
+      for (int j = 0; j < G.n_chunks; ++j) p.plane_lo[j] = G.arg[j];
+      p.n_plane_lo = p.n_plane;
+    } else {
+      const int skip_n = has_skip(ctx) ? 4 : 0;
+      for (int j = 0; j < G.n_chunks; ++j) p.plane_lo[j] = static_cast<uint8_t>(j < 4 ? skip_n + j : j - 4);
+      p.n_plane_lo = skip_n + 4;
+    }
   }
 }
 
-static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const ChainProg& prog_in, const ChainIO& io,
-                       cudaStream_t stream, bool bwd = false) {
-  es_ctx::Timed t{kind, io.n_points, nullptr, nullptr};
-  ChainProg prog = prog_in;
-  if (io.stash_hi) apply_plane_mode(ctx, kind, prog);
-  ChainIO io2 = io;
-  io2.trace = ctx->trace_dev;
-  {
-    const char* f = getenv("ES_DEBUG_FLAGS");
-    io2.debug_flags = f ? atoi(f) : 0;
-  }
+static int timer_begin(es_ctx* ctx, int kind, long long points, cudaStream_t stream, es_ctx::Timed& t) {
+  t = es_ctx::Timed{kind, points, nullptr, nullptr};
   if (ctx->profiling) {
     CU(cudaEventCreate(&t.e0));
     CU(cudaEventCreate(&t.e1));
     CU(cudaEventRecord(t.e0, stream));
   }
-  CU(launch_mlp_chain(chain, tangent, ctx->cfg.use_deform != 0, prog, io2, ctx->n_sms, stream, bwd));
+  return 0;
+}
+static int timer_end(es_ctx* ctx, cudaStream_t stream, es_ctx::Timed& t) {
   ++ctx->launches;
   if (ctx->profiling) {
     CU(cudaEventRecord(t.e1, stream));
     ctx->timed.push_back(t);
   }
   return 0;
+}
+
+static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const ChainProg& prog_in, const ChainIO& io,
+                       cudaStream_t stream, bool bwd = false, int inadj_k = 0) {
+  ChainProg prog = prog_in;
+  if (bwd || io.dump_hi) apply_plane_mode(ctx, kind, inadj_k, prog);
+  ChainIO io2 = io;
+  io2.trace = ctx->trace_dev;
+  io2.debug_flags = ctx->debug_flags;
+  es_ctx::Timed t;
+  if (int r = timer_begin(ctx, kind, io.n_points, stream, t)) return r;
+  CU(launch_mlp_chain(chain, tangent, ctx->cfg.use_deform != 0, prog, io2, ctx->n_sms, stream, bwd));
+  return timer_end(ctx, stream, t);
 }
 
 static int check_loaded(es_ctx* ctx, bool need_color) {
@@ -595,13 +857,32 @@ int es_sdf_query(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int
   io.t_div = t ? t_div : 1;
   io.t_stride = t ? t_stride : 0;
   io.out_sdf = sdf_out;
-  return timed_chain(ctx, 2, CHAIN_SDF, false, ctx->prog_sdfq, io, static_cast<cudaStream_t>(stream));
+  return timed_chain(ctx, K_SDFQ, CHAIN_SDF, false, ctx->prog_sdfq, io, static_cast<cudaStream_t>(stream));
+}
+
+// plane records of one training forward over n points, carved from the caller's stash buffer
+struct StashLayout {
+  long long tiles_g, tiles_c;
+  size_t geom_hi, geom_lo, color_hi, color_lo, total;  // byte offsets (lo = 0-sized unless full planes) and total
+};
+static StashLayout stash_layout(const es_ctx* ctx, int64_t n) {
+  StashLayout s{};
+  s.tiles_g = (n + 31) / 32;
+  s.tiles_c = (n + TILE_ROWS - 1) / TILE_ROWS;
+  const size_t g = static_cast<size_t>(s.tiles_g) * ctx->lay_geom.n_dump * SLOT_HALF_BYTES;
+  const size_t c = static_cast<size_t>(s.tiles_c) * ctx->lay_color.n_dump * SLOT_HALF_BYTES;
+  size_t off = 0;
+  s.geom_hi = off; off += g;
+  s.geom_lo = off; off += ctx->full_planes ? g : 0;
+  s.color_hi = off; off += c;
+  s.color_lo = off; off += ctx->full_planes ? c : 0;
+  s.total = off + 256;
+  return s;
 }
 
 static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
                               const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
-                              float* sdf, float* g_c, float* feat, float* rgb, uint16_t* gs_hi, uint16_t* gs_lo,
-                              uint16_t* cs_hi, uint16_t* cs_lo, void* stream_) {
+                              float* sdf, float* g_c, float* feat, float* rgb, uint8_t* stash, void* stream_) {
   if (!ctx || n < 0 || t_div <= 0) return ES_E_BADARG;
   if (n == 0) return 0;
   if (!x) return ES_E_BADARG;
@@ -610,22 +891,25 @@ static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64
   if (ctx->cfg.use_deform && !t) return fail(ctx, ES_E_BADARG, "time pointer required with use_deform");
   if (int r = check_loaded(ctx, want_color)) return r;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool deform = ctx->cfg.use_deform != 0;
   // scratch for whatever the caller did not ask for but the colour chain needs
   size_t need = 0;
   {
     Carver c(nullptr);
     if (!x_c) c.take<float>(n * 3);
-    if (!jac && ctx->cfg.use_deform) c.take<float>(n * 9);
+    if (!jac && deform) c.take<float>(n * 9);
     if (!g_c) c.take<float>(n * 3);
     if (!feat) c.take<float>(n * HID);
     need = c.off + 256;
   }
   if (int r = ensure_ws(ctx, need)) return r;
   Carver c(ctx->ws);
+  float* jac_out = jac;
   if (!x_c) x_c = c.take<float>(n * 3);
-  if (!jac && ctx->cfg.use_deform) jac = c.take<float>(n * 9);
+  if (!jac && deform) jac = c.take<float>(n * 9);
   if (!g_c) g_c = c.take<float>(n * 3);
   if (!feat) feat = c.take<float>(n * HID);
+  const StashLayout sl = stash_layout(ctx, n);
 
   ChainIO io{};
   io.n_points = n;
@@ -635,23 +919,22 @@ static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64
   io.t_div = t ? t_div : 1;
   io.t_stride = t ? t_stride : 0;
   io.out_xc = x_c;
-  io.out_jac = ctx->cfg.use_deform ? jac : nullptr;
+  io.out_jac = deform ? jac : nullptr;
   io.out_sdf = sdf;
   io.out_gc = g_c;
   io.out_feat = feat;
-  io.stash_hi = gs_hi;
-  io.stash_lo = gs_lo;
-  io.stash_rows = ((n + 31) / 32) * TILE_ROWS;
-  if (int r = timed_chain(ctx, 0, CHAIN_SDF, true, ctx->prog_geom, io, stream)) return r;
-  if (!ctx->cfg.use_deform)  // canonical = observed space (endosurf.py:576-577)
+  if (stash) {
+    io.dump_hi = stash + sl.geom_hi;
+    io.dump_lo = ctx->full_planes ? stash + sl.geom_lo : nullptr;
+  }
+  if (int r = timed_chain(ctx, K_GEOM, CHAIN_SDF, true, ctx->prog_geom, io, stream)) return r;
+  if (!deform) {
+    // canonical = observed space, J = I (endosurf.py:576-577, :626-630)
     CU(cudaMemcpyAsync(x_c, x, static_cast<size_t>(n) * 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-  if (!ctx->cfg.use_deform && jac) {
-    // J = I without a deformation network (endosurf.py:626-630)
-    static const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    std::vector<float> h(static_cast<size_t>(n) * 9);
-    for (int64_t i = 0; i < n; ++i) std::memcpy(&h[i * 9], eye, sizeof(eye));
-    CU(cudaMemcpyAsync(jac, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
-    CU(cudaStreamSynchronize(stream));
+    if (jac_out) {
+      CU(launch_fill_identity_jac(jac_out, n, stream));
+      ++ctx->launches;
+    }
   }
   if (want_color) {
     ChainIO ic{};
@@ -659,16 +942,17 @@ static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64
     ic.err = ctx->err_dev;
     ic.x_c = x_c;
     ic.g_c = g_c;
-    ic.jac = ctx->cfg.use_deform ? jac : nullptr;
+    ic.jac = deform ? jac : nullptr;
     ic.dirs = dirs;
     ic.dir_div = dir_div;
     ic.dir_stride = dir_stride;
     ic.feat = feat;
     ic.out_rgb = rgb;
-    ic.stash_hi = cs_hi;
-    ic.stash_lo = cs_lo;
-    ic.stash_rows = ((n + TILE_ROWS - 1) / TILE_ROWS) * TILE_ROWS;
-    if (int r = timed_chain(ctx, 1, CHAIN_COLOR, false, ctx->prog_color, ic, stream)) return r;
+    if (stash) {
+      ic.dump_hi = stash + sl.color_hi;
+      ic.dump_lo = ctx->full_planes ? stash + sl.color_lo : nullptr;
+    }
+    if (int r = timed_chain(ctx, K_COLOR, CHAIN_COLOR, false, ctx->prog_color, ic, stream)) return r;
   }
   return 0;
 }
@@ -677,59 +961,604 @@ int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div,
                      int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac, float* sdf, float* g_c,
                      float* feat, float* rgb, void* stream) {
   return point_forward_impl(ctx, x, t, t_div, t_stride, dirs, dir_div, dir_stride, n, x_c, jac, sdf, g_c, feat, rgb,
-                            nullptr, nullptr, nullptr, nullptr, stream);
+                            nullptr, stream);
 }
 
-int es_train_layout(const es_ctx* ctx, int64_t n, int64_t* out6) {
-  if (!ctx || !out6 || n < 0) return ES_E_BADARG;
-  out6[0] = ((n + 31) / 32) * TILE_ROWS;                       // geometry stash rows (4 rows per point)
-  out6[1] = ctx->prog_geom.n_layers;                           // geometry stash slots
-  out6[2] = ((n + TILE_ROWS - 1) / TILE_ROWS) * TILE_ROWS;     // colour stash rows
-  out6[3] = ctx->prog_color.n_layers + 1;                      // colour stash slots (+ output-layer input)
-  out6[4] = ctx->cfg.n_layers - 1;                             // zbar slots of each reverse chain (forward layer m)
-  out6[5] = ctx->cfg.use_deform ? ctx->cfg.n_layers - 1 : 0;   // geometry slot offset of the sdf layers
-  return 0;
-}
-
-int es_point_forward_train(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
-                           const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
-                           float* sdf, float* g_c, float* feat, float* rgb, uint16_t* geom_stash_hi,
-                           uint16_t* geom_stash_lo, uint16_t* color_stash_hi, uint16_t* color_stash_lo, void* stream) {
-  if (!x_c || !sdf || !g_c || !feat || !geom_stash_hi || !geom_stash_lo) return ES_E_BADARG;
-  if (rgb && (!color_stash_hi || !color_stash_lo)) return ES_E_BADARG;
-  return point_forward_impl(ctx, x, t, t_div, t_stride, dirs, dir_div, dir_stride, n, x_c, jac, sdf, g_c, feat, rgb,
-                            geom_stash_hi, geom_stash_lo, color_stash_hi, color_stash_lo, stream);
-}
-
-int es_point_backward(es_ctx* ctx, int net, int64_t n, const uint16_t* stash_hi, const uint16_t* stash_lo,
-                      const float* adj, const float* adj_feat, uint16_t* zbar_hi, uint16_t* zbar_lo, void* stream) {
-  if (!ctx || net < 0 || net > 2 || n < 0 || !stash_hi || !stash_lo || !adj || !zbar_hi || !zbar_lo)
-    return ES_E_BADARG;
-  if (net == ES_NET_SDF && !adj_feat) return fail(ctx, ES_E_BADARG, "adj_feat required for the sdf chain");
-  if (net == ES_NET_DEFORM && !ctx->cfg.use_deform) return fail(ctx, ES_E_BADARG, "no deformation network");
-  if (int r = check_loaded(ctx, true)) return r;
-  if (n == 0) return 0;
-  ChainIO io{};
-  io.n_points = n;
-  io.err = ctx->err_dev;
-  io.stash_hi = const_cast<uint16_t*>(stash_hi);
-  io.stash_lo = const_cast<uint16_t*>(stash_lo);
-  const bool tangent = net != ES_NET_COLOR;
-  io.stash_rows = tangent ? ((n + 31) / 32) * TILE_ROWS : ((n + TILE_ROWS - 1) / TILE_ROWS) * TILE_ROWS;
-  io.zbar_hi = zbar_hi;
-  io.zbar_lo = zbar_lo;
-  io.adj = adj;
-  io.adj_feat = adj_feat;
-  io.t_div = 1;
-  io.dir_div = 1;
-  return timed_chain(ctx, 3 + net, tangent ? CHAIN_SDF : CHAIN_COLOR, tangent, ctx->prog_rev[net], io,
-                     static_cast<cudaStream_t>(stream), true);
-}
-
+// =================================================================================================================
+// training (differentiable) path
+// =================================================================================================================
 int es_set_plane_mode(es_ctx* ctx, int32_t full_planes) {
   if (!ctx) return ES_E_BADARG;
   ctx->full_planes = full_planes != 0;
   return 0;
+}
+
+int es_train_stash_bytes(const es_ctx* ctx, int64_t n, int64_t* out) {
+  if (!ctx || !out || n < 0) return ES_E_BADARG;
+  *out = static_cast<int64_t>(stash_layout(ctx, n).total);
+  return 0;
+}
+
+int es_point_train_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
+                           const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
+                           float* sdf, float* g_c, float* rgb, uint8_t* stash, void* stream) {
+  if (!x_c || !sdf || !g_c || !rgb || !stash || (ctx && ctx->cfg.use_deform && !jac)) return ES_E_BADARG;
+  return point_forward_impl(ctx, x, t, t_div, t_stride, dirs, dir_div, dir_stride, n, x_c, jac, sdf, g_c, nullptr, rgb,
+                            stash, stream);
+}
+
+namespace {
+
+// zbar record index (first chunk) of forward layer m of network net; m = L-1 selects the sdf feature rows
+int zbar_chunk0(const es_ctx* ctx, int net, int m) {
+  const int L = ctx->cfg.n_layers;
+  const int nr = ctx->rev_layers[net];
+  if (m == 0) return 4 * nr;                         // POST_BWD_DUMP result
+  if (net == ES_NET_SDF) return m == L - 1 ? 0 : 4 * (1 + (L - 2 - m));
+  return 4 * (L - 2 - m);
+}
+
+// base-pointer slots of WgradBases
+enum { WB_ZBAR_HI = 0 /* + net */, WB_ZBAR_LO = 3 /* + net */, WB_GEOM_HI = 6, WB_GEOM_LO = 7, WB_COLOR_HI = 8,
+       WB_COLOR_LO = 9 };
+
+// Build (or fetch) the weight-gradient work list for n points in the current plane mode.
+int get_wgrad_plan(es_ctx* ctx, int64_t n, es_ctx::WgradPlan** out) {
+  for (auto& wp : ctx->wplans)
+    if (wp.n == n && wp.full == ctx->full_planes) {
+      *out = &wp;
+      return 0;
+    }
+  const es_net_config& cfg = ctx->cfg;
+  const int L = cfg.n_layers;
+  const int Ld = cfg.use_deform ? L - 1 : 0;
+  const StashLayout sl = stash_layout(ctx, n);
+  const bool full = ctx->full_planes != 0;
+  struct Proto {
+    int net, layer, mhalf, n_b, a_chunk, b_chunk, bias_mode, row_off, n_out, n_in;
+    long long tiles;
+    float mul;
+    std::vector<int> colmap;
+  };
+  std::vector<Proto> protos;
+  for (int net = 0; net < 3; ++net) {
+    if (net == ES_NET_DEFORM && !cfg.use_deform) continue;
+    const NetPlan& P = ctx->plan[net];
+    const es_ctx::FwdLayout& lay = net == ES_NET_COLOR ? ctx->lay_color : ctx->lay_geom;
+    const ChainProg& fp = net == ES_NET_COLOR ? ctx->prog_color : ctx->prog_geom;
+    const int l0 = net == ES_NET_SDF ? Ld : 0;
+    const int n_mma = static_cast<int>(P.packs.size());  // hidden layers (+ sdf feature layer)
+    for (int m = 0; m < n_mma; ++m) {
+      const LayerPack& K = P.packs[m];
+      const LayerProg& G = fp.layer[l0 + m];
+      const bool feat_rows = net == ES_NET_SDF && m == L - 1;
+      // runs of consecutive record chunks, at most 4 per group
+      int k = 0, koff = 0;
+      while (k < G.n_chunks) {
+        int len = 1;
+        while (k + len < G.n_chunks && len < 4 && lay.in_idx[l0 + m][k + len] == lay.in_idx[l0 + m][k] + len) ++len;
+        std::vector<int> cm;
+        for (int j = 0; j < len; ++j) {
+          const int width = G.nsub[k + j] * SUB_K;
+          for (int q = 0; q < 64; ++q) cm.push_back(q < width ? K.colmap[koff + q] : -1);
+          koff += width;
+        }
+        for (int h = 0; h < 2; ++h) {
+          if (128 * h >= K.n_out) continue;
+          Proto pr;
+          pr.net = net;
+          pr.layer = m;
+          pr.mhalf = h;
+          pr.n_b = len;
+          pr.a_chunk = zbar_chunk0(ctx, net, m) + 2 * h;
+          pr.b_chunk = lay.in_idx[l0 + m][k];
+          pr.bias_mode = k == 0 ? (net == ES_NET_COLOR ? 1 : 2) : 0;  // bias sums ride with the first group
+          pr.row_off = feat_rows ? 1 : 0;
+          pr.n_out = K.n_out;
+          pr.n_in = P.in_dims[m];
+          pr.tiles = net == ES_NET_COLOR ? sl.tiles_c : sl.tiles_g;
+          pr.mul = K.scale;
+          pr.colmap = cm;
+          protos.push_back(pr);
+        }
+        k += len;
+      }
+    }
+  }
+  const int n_terms = full ? 3 : 1;
+  long long total_work = 0;
+  for (auto& pr : protos) total_work += pr.tiles * n_terms;
+  const long long slice_tiles = std::max<long long>(16, (total_work + ctx->n_sms * 4 - 1) / (ctx->n_sms * 4));
+  es_ctx::WgradPlan wp;
+  wp.n = n;
+  wp.full = ctx->full_planes;
+  std::vector<WgradItem> items;
+  std::vector<int> colmaps;
+  if (protos.size() > sizeof(WgradJobs::j) / sizeof(WgradJob)) return fail(ctx, ES_E_UNSUPPORTED, "too many wgrad jobs");
+  for (auto& pr : protos) {
+    WgradJob jb{};
+    jb.slot0 = static_cast<int>(items.size());
+    jb.n_cols = 64 * pr.n_b;
+    jb.row0 = 128 * pr.mhalf;
+    jb.row_off = pr.row_off;
+    jb.n_out = pr.n_out;
+    jb.n_in = pr.n_in;
+    jb.mul = pr.mul;
+    jb.colmap = reinterpret_cast<const int*>(static_cast<uintptr_t>(colmaps.size()));  // offset, patched below
+    colmaps.insert(colmaps.end(), pr.colmap.begin(), pr.colmap.end());
+    const int rec_a = ctx->prog_rev[pr.net].n_dump;
+    const bool color = pr.net == ES_NET_COLOR;
+    const int rec_b = color ? ctx->lay_color.n_dump : ctx->lay_geom.n_dump;
+    int n_bias = 0;
+    // terms: (A hi, B hi) [+ (A lo, B hi) + (A hi, B lo) with every lo plane kept]
+    for (int term = 0; term < n_terms; ++term) {
+      const bool a_lo = term == 1, b_lo = term == 2;
+      for (long long t0 = 0; t0 < pr.tiles; t0 += slice_tiles) {
+        WgradItem it{};
+        it.a_buf = (a_lo ? WB_ZBAR_LO : WB_ZBAR_HI) + pr.net;
+        it.b_buf = color ? (b_lo ? WB_COLOR_LO : WB_COLOR_HI) : (b_lo ? WB_GEOM_LO : WB_GEOM_HI);
+        it.a_stride = static_cast<long long>(rec_a) * SLOT_HALF_BYTES;
+        it.b_stride = static_cast<long long>(rec_b) * SLOT_HALF_BYTES;
+        it.a_off = static_cast<long long>(pr.a_chunk) * SLOT_HALF_BYTES;
+        it.b_off = static_cast<long long>(pr.b_chunk) * SLOT_HALF_BYTES;
+        it.tile0 = static_cast<int>(t0);
+        it.tile1 = static_cast<int>(std::min<long long>(pr.tiles, t0 + slice_tiles));
+        it.n_b = pr.n_b;
+        it.bias_mode = (pr.bias_mode && term < 2) ? pr.bias_mode : 0;
+        it.out = static_cast<int>(items.size());
+        if (it.bias_mode) ++n_bias;
+        items.push_back(it);
+      }
+    }
+    jb.n_slices = static_cast<int>(items.size()) - jb.slot0;
+    jb.n_bias_slices = n_bias;
+    wp.jobs.push_back(jb);
+    wp.job_net.push_back(pr.net);
+    wp.job_layer.push_back(pr.layer);
+  }
+  wp.n_items = static_cast<int>(items.size());
+  CU(cudaMalloc(&wp.items_dev, std::max<size_t>(1, items.size()) * sizeof(WgradItem)));
+  CU(cudaMalloc(&wp.colmaps_dev, std::max<size_t>(1, colmaps.size()) * sizeof(int)));
+  CU(cudaMemcpy(wp.items_dev, items.data(), items.size() * sizeof(WgradItem), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(wp.colmaps_dev, colmaps.data(), colmaps.size() * sizeof(int), cudaMemcpyHostToDevice));
+  for (auto& jb : wp.jobs) jb.colmap = wp.colmaps_dev + reinterpret_cast<uintptr_t>(jb.colmap);
+  if (ctx->wplans.size() >= 16) {  // bounded cache
+    cudaFree(ctx->wplans.front().items_dev);
+    cudaFree(ctx->wplans.front().colmaps_dev);
+    ctx->wplans.erase(ctx->wplans.begin());
+  }
+  ctx->wplans.push_back(std::move(wp));
+  *out = &ctx->wplans.back();
+  return 0;
+}
+
+struct BwdIn {
+  int64_t n;
+  const float* dirs;
+  int64_t dir_div, dir_stride;
+  const float* x_c;
+  const float* jac;
+  const float* g_c;
+  const uint8_t* stash;
+  float* adj_color;   // [n][4]
+  float* adj_sdf;     // [4n][4]
+  float* adj_deform;  // [4n][4] or null
+};
+
+// scratch of one backward call, carved from the workspace after the caller's own buffers
+struct BwdScratch {
+  size_t bytes = 0;
+  float* feat_bar = nullptr;
+  uint8_t* zbar_hi[3] = {nullptr, nullptr, nullptr};
+  uint8_t* zbar_lo[3] = {nullptr, nullptr, nullptr};
+  float* partial = nullptr;
+  float* bias_partial = nullptr;
+  float* small_part = nullptr;
+  float* gw_eff[3][16] = {};
+};
+void carve_backward(const es_ctx* ctx, int64_t n, int n_items, Carver& c, BwdScratch& s) {
+  const StashLayout sl = stash_layout(ctx, n);
+  const bool full = ctx->full_planes != 0;
+  s.feat_bar = c.take<float>(n * HID);
+  for (int net = 0; net < 3; ++net) {
+    if (net == ES_NET_DEFORM && !ctx->cfg.use_deform) continue;
+    const long long tiles = net == ES_NET_COLOR ? sl.tiles_c : sl.tiles_g;
+    const int rec = ctx->prog_rev[net].n_dump;
+    s.zbar_hi[net] = c.take<uint8_t>(static_cast<size_t>(tiles) * rec * SLOT_HALF_BYTES);
+    const int rec_lo = full ? rec : (net == ES_NET_DEFORM ? 0 : (has_skip(ctx) ? 8 : 4));
+    s.zbar_lo[net] = c.take<uint8_t>(static_cast<size_t>(tiles) * rec_lo * SLOT_HALF_BYTES + 16);
+  }
+  s.partial = c.take<float>(static_cast<size_t>(n_items) * TILE_ROWS * HID);
+  s.bias_partial = c.take<float>(static_cast<size_t>(n_items) * TILE_ROWS);
+  s.small_part = c.take<float>(static_cast<size_t>(3) * 2 * ctx->n_sms * (4 * HID + 4));
+  for (int net = 0; net < 3; ++net)
+    for (int l = 0; l < ctx->cfg.n_layers; ++l)
+      s.gw_eff[net][l] = c.take<float>(static_cast<size_t>(ctx->plan[net].out_dims[l]) * ctx->plan[net].in_dims[l]);
+  s.bytes = c.off + 256;
+}
+
+// The reverse pass of the point pipeline from prepared adjoint rows to d loss / d (weight_v, weight_g, bias).
+int backward_core(es_ctx* ctx, const BwdIn& a, const BwdScratch& s, es_ctx::WgradPlan& wp, const es_train_params* prm,
+                  cudaStream_t stream) {
+  const es_net_config& cfg = ctx->cfg;
+  const int L = cfg.n_layers;
+  const bool deform = cfg.use_deform != 0;
+  const int64_t n = a.n;
+  const StashLayout sl = stash_layout(ctx, n);
+  const bool full = ctx->full_planes != 0;
+  es_ctx::Timed t;
+  CU(cudaMemsetAsync(ctx->amax_dev, 0, 4 * sizeof(unsigned int), stream));
+  for (int net = 0; net < 3; ++net)
+    for (int l = 0; l < L; ++l)
+      CU(cudaMemsetAsync(s.gw_eff[net][l], 0,
+                         static_cast<size_t>(ctx->plan[net].out_dims[l]) * ctx->plan[net].in_dims[l] * sizeof(float),
+                         stream));
+  auto rev_chain = [&](int net, const float* adj, const float* adj_feat) -> int {
+    ChainIO io{};
+    io.n_points = n;
+    io.err = ctx->err_dev;
+    io.adj = adj;
+    io.adj_feat = adj_feat;
+    io.scale = ctx->scale_dev + net;
+    const bool color = net == ES_NET_COLOR;
+    io.gate_hi = a.stash + (color ? sl.color_hi : sl.geom_hi);
+    io.gate_lo = full ? a.stash + (color ? sl.color_lo : sl.geom_lo) : nullptr;
+    io.dump_hi = s.zbar_hi[net];
+    io.dump_lo = s.zbar_lo[net];
+    io.t_div = 1;
+    io.dir_div = 1;
+    return timed_chain(ctx, K_REV_DEFORM + net, color ? CHAIN_COLOR : CHAIN_SDF, !color, ctx->prog_rev[net], io, stream,
+                       true);
+  };
+  auto inadj = [&](int k) -> int {
+    const int net = k == 0 ? ES_NET_SDF : ES_NET_COLOR;
+    ChainIO io{};
+    io.n_points = n;
+    io.err = ctx->err_dev;
+    io.scale = ctx->scale_dev + net;
+    io.plane_hi = s.zbar_hi[net];
+    io.plane_lo = s.zbar_lo[net];
+    io.x_c = a.x_c;
+    io.g_c = a.g_c;
+    io.jac = deform ? a.jac : nullptr;
+    io.dirs = a.dirs;
+    io.dir_div = a.dir_div;
+    io.dir_stride = a.dir_stride;
+    io.feat_bar = s.feat_bar;
+    io.adj_sdf = a.adj_sdf;
+    io.adj_deform = deform ? a.adj_deform : nullptr;
+    io.amax_bits = ctx->amax_dev + ES_NET_SDF;
+    io.t_div = 1;
+    return timed_chain(ctx, K_INADJ, k == 0 ? CHAIN_SDF : CHAIN_COLOR, k == 0, ctx->prog_inadj[k], io, stream, true, k);
+  };
+  auto set_scale = [&](int net, const float* adj, long long count) -> int {
+    CU(launch_amax(adj, count, ctx->amax_dev + net, stream));
+    CU(launch_scale_from_amax(ctx->amax_dev + net, ctx->scale_dev + net, stream));
+    ctx->launches += 2;
+    return 0;
+  };
+
+  // ---- colour network
+  if (int r = set_scale(ES_NET_COLOR, a.adj_color, n * 4)) return r;
+  if (int r = rev_chain(ES_NET_COLOR, a.adj_color, nullptr)) return r;
+  if (int r = inadj(1)) return r;   // feat_bar (+ its amax into the sdf slot)
+  if (int r = inadj(2)) return r;   // adj_sdf += d/d g_c ; adj_deform += d/d (x_c, J)
+  // ---- sdf network
+  if (int r = set_scale(ES_NET_SDF, a.adj_sdf, n * 16)) return r;
+  if (int r = rev_chain(ES_NET_SDF, a.adj_sdf, s.feat_bar)) return r;
+  // ---- deformation network
+  if (deform) {
+    if (int r = inadj(0)) return r;  // adj_deform += d/d x_c through enc6(x_c)
+    if (int r = set_scale(ES_NET_DEFORM, a.adj_deform, n * 16)) return r;
+    if (int r = rev_chain(ES_NET_DEFORM, a.adj_deform, nullptr)) return r;
+  }
+
+  // ---- 3-wide output layers (fp32 adjoints x kept layer inputs, CUDA cores)
+  {
+    if (int r = timer_begin(ctx, K_SMALLM, n, stream, t)) return r;
+    const int nb_c = smallm_blocks(sl.tiles_c, ctx->n_sms), nb_g = smallm_blocks(sl.tiles_g, ctx->n_sms);
+    const size_t per = static_cast<size_t>(2) * ctx->n_sms * (4 * HID + 4);
+    const long long gs = static_cast<long long>(ctx->lay_geom.n_dump) * SLOT_HALF_BYTES;
+    const long long cs = static_cast<long long>(ctx->lay_color.n_dump) * SLOT_HALF_BYTES;
+    // colour output layer
+    CU(launch_smallm_wgrad(a.stash + sl.color_hi + static_cast<size_t>(ctx->lay_color.tail) * SLOT_HALF_BYTES, cs,
+                           sl.tiles_c, a.adj_color, 0, n, s.small_part, nb_c, stream));
+    CU(launch_smallm_reduce(s.small_part, nb_c, 0, 3, s.gw_eff[ES_NET_COLOR][L - 1], prm->grad_b[ES_NET_COLOR][L - 1],
+                            0, HID, stream));
+    // sdf row of the sdf output layer: input = the feature layer's input chunks
+    const int Ld = deform ? L - 1 : 0;
+    CU(launch_smallm_wgrad(
+        a.stash + sl.geom_hi + static_cast<size_t>(ctx->lay_geom.in_idx[Ld + L - 1][0]) * SLOT_HALF_BYTES, gs,
+        sl.tiles_g, a.adj_sdf, 1, n, s.small_part + per, nb_g, stream));
+    CU(launch_smallm_reduce(s.small_part + per, nb_g, 3, 1, s.gw_eff[ES_NET_SDF][L - 1], prm->grad_b[ES_NET_SDF][L - 1],
+                            0, HID, stream));
+    ctx->launches += 3;
+    if (deform) {
+      CU(launch_smallm_wgrad(a.stash + sl.geom_hi + static_cast<size_t>(ctx->lay_geom.tail) * SLOT_HALF_BYTES, gs,
+                             sl.tiles_g, a.adj_deform, 1, n, s.small_part + 2 * per, nb_g, stream));
+      CU(launch_smallm_reduce(s.small_part + 2 * per, nb_g, 0, 3, s.gw_eff[ES_NET_DEFORM][L - 1],
+                              prm->grad_b[ES_NET_DEFORM][L - 1], 0, HID, stream));
+      ctx->launches += 2;
+    }
+    if (int r = timer_end(ctx, stream, t)) return r;
+  }
+
+  // ---- 256-wide layers: split-K tcgen05 weight gradients over the plane records, then reduce + scatter
+  {
+    WgradBases bases{};
+    for (int net = 0; net < 3; ++net) {
+      bases.p[WB_ZBAR_HI + net] = s.zbar_hi[net];
+      bases.p[WB_ZBAR_LO + net] = s.zbar_lo[net];
+    }
+    bases.p[WB_GEOM_HI] = a.stash + sl.geom_hi;
+    bases.p[WB_GEOM_LO] = a.stash + sl.geom_lo;
+    bases.p[WB_COLOR_HI] = a.stash + sl.color_hi;
+    bases.p[WB_COLOR_LO] = a.stash + sl.color_lo;
+    if (int r = timer_begin(ctx, K_WGRAD, n, stream, t)) return r;
+    CU(launch_wgrad(wp.items_dev, wp.n_items, bases, s.partial, s.bias_partial, ctx->wgrad_lbo, ctx->wgrad_sbo,
+                    ctx->err_dev, stream));
+    if (int r = timer_end(ctx, stream, t)) return r;
+    WgradJobs jobs{};
+    jobs.n = static_cast<int>(wp.jobs.size());
+    for (int j = 0; j < jobs.n; ++j) {
+      WgradJob jb = wp.jobs[j];
+      const int net = wp.job_net[j], layer = wp.job_layer[j];
+      jb.gw = s.gw_eff[net][layer];
+      jb.gb = jb.n_bias_slices > 0 ? prm->grad_b[net][layer] : nullptr;
+      jb.scale = ctx->scale_dev + net;
+      jobs.j[j] = jb;
+    }
+    if (int r = timer_begin(ctx, K_WREDUCE, n, stream, t)) return r;
+    CU(launch_wgrad_reduce(jobs, s.partial, s.bias_partial, stream));
+    // weight-norm backward: d W -> d (weight_g, weight_v)
+    WnLayers tab{};
+    int max_rows = 0;
+    for (int net = 0; net < 3; ++net) {
+      if (net == ES_NET_DEFORM && !deform) continue;
+      for (int l = 0; l < L; ++l) {
+        WnLayer& W = tab.l[tab.n++];
+        W.v = prm->v[net][l];
+        W.g = prm->g[net][l];
+        W.gw = s.gw_eff[net][l];
+        W.gv = prm->grad_v[net][l];
+        W.gg = prm->grad_g[net][l];
+        W.n_out = ctx->plan[net].out_dims[l];
+        W.n_in = ctx->plan[net].in_dims[l];
+        max_rows = std::max(max_rows, W.n_out);
+      }
+    }
+    CU(launch_wn_backward(tab, max_rows, stream));
+    ++ctx->launches;
+    if (int r = timer_end(ctx, stream, t)) return r;
+  }
+  return 0;
+}
+
+int check_train_params(es_ctx* ctx, const es_train_params* prm) {
+  if (!prm) return ES_E_BADARG;
+  for (int net = 0; net < 3; ++net) {
+    if (net == ES_NET_DEFORM && !ctx->cfg.use_deform) continue;
+    if (!prm->v[net] || !prm->g[net] || !prm->grad_v[net] || !prm->grad_g[net] || !prm->grad_b[net])
+      return fail(ctx, ES_E_BADARG, "es_train_params: null table");
+    for (int l = 0; l < ctx->cfg.n_layers; ++l)
+      if (!prm->v[net][l] || !prm->g[net][l] || !prm->grad_v[net][l] || !prm->grad_g[net][l] || !prm->grad_b[net][l])
+        return fail(ctx, ES_E_BADARG, "es_train_params: null layer pointer");
+  }
+  return 0;
+}
+
+}  // namespace
+
+int es_point_train_backward(es_ctx* ctx, int64_t n, const float* dirs, int64_t dir_div, int64_t dir_stride,
+                            const float* x_c, const float* jac, const float* g_c, const float* rgb,
+                            const uint8_t* stash, const float* sdf_bar, const float* gc_bar, const float* jac_bar,
+                            const float* rgb_bar, const es_train_params* prm, void* stream_) {
+  if (!ctx || n < 0 || !x_c || !g_c || !rgb || !stash || !dirs || dir_div <= 0) return ES_E_BADARG;
+  if (ctx->cfg.use_deform && !jac) return ES_E_BADARG;
+  if (int r = check_train_params(ctx, prm)) return r;
+  if (int r = check_loaded(ctx, true)) return r;
+  if (n == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool deform = ctx->cfg.use_deform != 0;
+  es_ctx::WgradPlan* wp = nullptr;
+  if (int r = get_wgrad_plan(ctx, n, &wp)) return r;
+  BwdScratch s;
+  float *adj_c, *adj_s, *adj_d;
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver c(pass ? ctx->ws : nullptr);
+    adj_c = c.take<float>(n * 4);
+    adj_s = c.take<float>(n * 16);
+    adj_d = c.take<float>(deform ? n * 16 : 0);
+    carve_backward(ctx, n, wp->n_items, c, s);
+    if (!pass)
+      if (int r = ensure_ws(ctx, s.bytes)) return r;
+  }
+  CU(launch_point_adjoints(n, rgb, sdf_bar, gc_bar, deform ? jac_bar : nullptr, rgb_bar, adj_c, adj_s,
+                           deform ? adj_d : nullptr, stream));
+  ++ctx->launches;
+  BwdIn a{n, dirs, dir_div, dir_stride, x_c, jac, g_c, stash, adj_c, adj_s, deform ? adj_d : nullptr};
+  return backward_core(ctx, a, s, *wp, prm, stream);
+}
+
+int es_render_train_forward(es_ctx* ctx, const float* rays, int64_t n_rays, const float* z_vals, int32_t m,
+                            int32_t n_samples, float cos_anneal_ratio, const float* variance, float* x_c, float* jac,
+                            float* sdf, float* g_c, float* rgb, uint8_t* stash, const es_render_out* out,
+                            float* eik_den, void* stream_) {
+  if (!ctx || !rays || !z_vals || !variance || !x_c || !sdf || !g_c || !rgb || !stash || !out || !eik_den ||
+      n_rays < 0 || m < 1 || m > 256 || n_samples < 2)
+    return ES_E_BADARG;
+  if (!out->color_map || !out->depth_map || !out->gradients_o || !out->gradient_o_error || !out->weights ||
+      !out->weight_max || !out->cdf || !out->s_val)
+    return fail(ctx, ES_E_BADARG, "null output pointer");
+  if (ctx->cfg.use_deform && !jac) return ES_E_BADARG;
+  if (int r = check_loaded(ctx, true)) return r;
+  if (n_rays == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool deform = ctx->cfg.use_deform != 0;
+  const int64_t n = n_rays * m;
+  const float sample_dist = 2.0f / static_cast<float>(n_samples);
+  // mid-points and per-ray partials live past the scratch point_forward_impl carves for itself (feat)
+  const size_t fwd_need = static_cast<size_t>(n) * HID * sizeof(float) + 1024;
+  size_t off_pts, off_eik, need;
+  {
+    Carver c(nullptr);
+    c.off = fwd_need;
+    c.take<float>(n * 3);
+    off_pts = c.off - static_cast<size_t>(n) * 3 * sizeof(float);
+    c.take<float>(n_rays * 2);
+    off_eik = c.off - static_cast<size_t>(n_rays) * 2 * sizeof(float);
+    need = c.off + 256;
+  }
+  if (int r = ensure_ws(ctx, need)) return r;
+  float* pts = reinterpret_cast<float*>(ctx->ws + off_pts);
+  float* eik = reinterpret_cast<float*>(ctx->ws + off_eik);
+  RayGeom rg{rays, n_rays};
+  CU(launch_points_from_z(rg, z_vals, m, 1, sample_dist, pts, stream));
+  ++ctx->launches;
+  if (int r = point_forward_impl(ctx, pts, rays + 8, m, 9, rays + 3, m, 9, n, x_c, deform ? jac : nullptr, sdf, g_c,
+                                 nullptr, rgb, stash, stream_))
+    return r;
+  es_ctx::Timed t;
+  if (int r = timer_begin(ctx, K_COMPOSITE, n, stream, t)) return r;
+  CompositeOut co;
+  co.color_map = out->color_map;
+  co.depth_map = out->depth_map;
+  co.gradients_o = out->gradients_o;
+  co.weights = out->weights;
+  co.cdf = out->cdf;
+  co.weight_max = out->weight_max;
+  co.eik_partial = eik;
+  co.s_val = out->s_val;
+  CU(launch_composite(rg, z_vals, m, sample_dist, sdf, g_c, deform ? jac : nullptr, rgb, variance, cos_anneal_ratio,
+                      co, stream));
+  CU(launch_eikonal_reduce(eik, n_rays, out->gradient_o_error, eik_den, stream));
+  ++ctx->launches;
+  return timer_end(ctx, stream, t);
+}
+
+int es_render_train_backward(es_ctx* ctx, const float* rays, int64_t n_rays, const float* z_vals, int32_t m,
+                             int32_t n_samples, float cos_anneal_ratio, const float* variance, const float* x_c,
+                             const float* jac, const float* sdf, const float* g_c, const float* rgb,
+                             const uint8_t* stash, const float* eik_den, const es_render_grads* bar,
+                             const es_train_params* prm, float* variance_grad, void* stream_) {
+  if (!ctx || !rays || !z_vals || !variance || !x_c || !sdf || !g_c || !rgb || !stash || !eik_den || !bar ||
+      !variance_grad || n_rays < 0 || m < 1 || m > 256 || n_samples < 2)
+    return ES_E_BADARG;
+  if (ctx->cfg.use_deform && !jac) return ES_E_BADARG;
+  if (int r = check_train_params(ctx, prm)) return r;
+  if (int r = check_loaded(ctx, true)) return r;
+  if (n_rays == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool deform = ctx->cfg.use_deform != 0;
+  const int64_t n = n_rays * m;
+  const float sample_dist = 2.0f / static_cast<float>(n_samples);
+  es_ctx::WgradPlan* wp = nullptr;
+  if (int r = get_wgrad_plan(ctx, n, &wp)) return r;
+  BwdScratch s;
+  float *adj_c, *adj_s, *adj_d, *invs;
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver c(pass ? ctx->ws : nullptr);
+    adj_c = c.take<float>(n * 4);
+    adj_s = c.take<float>(n * 16);
+    adj_d = c.take<float>(deform ? n * 16 : 0);
+    invs = c.take<float>(n_rays);
+    carve_backward(ctx, n, wp->n_items, c, s);
+    if (!pass)
+      if (int r = ensure_ws(ctx, s.bytes)) return r;
+  }
+  es_ctx::Timed t;
+  if (int r = timer_begin(ctx, K_COMPOSITE, n, stream, t)) return r;
+  CompositeBwd cb{};
+  cb.color_bar = bar->color_map;
+  cb.depth_bar = bar->depth_map;
+  cb.go_bar = bar->gradients_o;
+  cb.weights_bar = bar->weights;
+  cb.cdf_bar = bar->cdf;
+  cb.sdf_bar = bar->sdf;
+  cb.rgb_bar = bar->sampled_color;
+  cb.eik_bar = bar->gradient_o_error;
+  cb.eik_den = eik_den;
+  cb.adj_color = adj_c;
+  cb.adj_sdf = adj_s;
+  cb.adj_deform = deform ? adj_d : nullptr;
+  cb.invs_partial = invs;
+  RayGeom rg{rays, n_rays};
+  CU(launch_composite_bwd(rg, z_vals, m, sample_dist, sdf, g_c, deform ? jac : nullptr, rgb, variance,
+                          cos_anneal_ratio, cb, stream));
+  CU(launch_sum_reduce(invs, n_rays, variance_grad, 0, stream));
+  ++ctx->launches;
+  if (int r = timer_end(ctx, stream, t)) return r;
+  BwdIn a{n, rays + 3, m, 9, x_c, jac, g_c, stash, adj_c, adj_s, deform ? adj_d : nullptr};
+  return backward_core(ctx, a, s, *wp, prm, stream);
+}
+
+int es_wgrad_probe(es_ctx* ctx, const uint8_t* zbar_rec, const uint8_t* in_rec, int64_t n_tiles, int32_t n_b,
+                   int32_t bias_mode, float* out, float* bias_out, void* stream_) {
+  if (!ctx || !zbar_rec || !in_rec || !out || n_tiles < 1 || n_b < 1 || n_b > 4 || bias_mode < 0 || bias_mode > 2)
+    return ES_E_BADARG;
+  if (bias_mode && !bias_out) return ES_E_BADARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  std::vector<WgradItem> items;
+  WgradJobs jobs{};
+  const long long slice = std::max<long long>(1, (n_tiles + 2) / 3);  // three slices: exercises the split-K reduce
+  for (int h = 0; h < 2; ++h) {
+    WgradJob jb{};
+    jb.slot0 = static_cast<int>(items.size());
+    for (long long t0 = 0; t0 < n_tiles; t0 += slice) {
+      WgradItem it{};
+      it.a_buf = 0;
+      it.b_buf = 1;
+      it.a_stride = 4LL * SLOT_HALF_BYTES;
+      it.b_stride = static_cast<long long>(n_b) * SLOT_HALF_BYTES;
+      it.a_off = 2LL * h * SLOT_HALF_BYTES;
+      it.b_off = 0;
+      it.tile0 = static_cast<int>(t0);
+      it.tile1 = static_cast<int>(std::min<long long>(n_tiles, t0 + slice));
+      it.n_b = n_b;
+      it.bias_mode = bias_mode;
+      it.out = static_cast<int>(items.size());
+      items.push_back(it);
+    }
+    jb.n_slices = static_cast<int>(items.size()) - jb.slot0;
+    jb.n_bias_slices = bias_mode ? jb.n_slices : 0;
+    jb.n_cols = 64 * n_b;
+    jb.row0 = 128 * h;
+    jb.n_out = 256;
+    jb.n_in = 64 * n_b;
+    jb.gw = out;
+    jb.gb = bias_mode ? bias_out : nullptr;
+    jb.mul = 1.f;
+    jobs.j[jobs.n++] = jb;
+  }
+  WgradItem* items_dev = nullptr;
+  float* partial = nullptr;
+  float* bias_partial = nullptr;
+  CU(cudaMalloc(&items_dev, items.size() * sizeof(WgradItem)));
+  CU(cudaMalloc(&partial, items.size() * TILE_ROWS * HID * sizeof(float)));
+  CU(cudaMalloc(&bias_partial, items.size() * TILE_ROWS * sizeof(float)));
+  CU(cudaMemcpy(items_dev, items.data(), items.size() * sizeof(WgradItem), cudaMemcpyHostToDevice));
+  WgradBases bases{};
+  bases.p[0] = zbar_rec;
+  bases.p[1] = in_rec;
+  CU(launch_wgrad(items_dev, static_cast<int>(items.size()), bases, partial, bias_partial, ctx->wgrad_lbo,
+                  ctx->wgrad_sbo, ctx->err_dev, stream));
+  CU(launch_wgrad_reduce(jobs, partial, bias_partial, stream));
+  ctx->launches += 2;
+  CU(cudaStreamSynchronize(stream));
+  CU(cudaFree(items_dev));
+  CU(cudaFree(partial));
+  CU(cudaFree(bias_partial));
+  return 0;
+}
+
+int es_debug_set(es_ctx* ctx, int32_t key, int32_t value) {
+  if (!ctx) return ES_E_BADARG;
+  switch (key) {
+    case 0: ctx->debug_flags = value; return 0;   // ES_ABLATE builds only
+    case 1: ctx->wgrad_lbo = value; return 0;     // MN-major descriptor strides of the weight-gradient kernel
+    case 2: ctx->wgrad_sbo = value; return 0;
+    default: return ES_E_BADARG;
+  }
 }
 
 int es_up_sample(es_ctx* ctx, const float* rays, int64_t n_rays, const float* z, const float* sdf, int32_t n,
@@ -871,7 +1700,7 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
       CU(cudaMemcpyAsync(out->z_vals + r0 * M, z, R * M * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }
   if (sample_only) return 0;
-  CU(launch_eikonal_reduce(eik, n_rays, out->gradient_o_error, stream));
+  CU(launch_eikonal_reduce(eik, n_rays, out->gradient_o_error, nullptr, stream));
   ++ctx->launches;
   return 0;
 }
@@ -889,6 +1718,7 @@ int es_profile_read(es_ctx* ctx, es_profile* out, void* stream) {
   for (auto& t : ctx->timed) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, t.e0, t.e1));
+    if (t.kind < 0 || t.kind >= K_NKINDS) continue;
     out->ms[t.kind] += ms;
     out->launches[t.kind] += 1;
     out->points[t.kind] += t.points;

@@ -127,6 +127,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 
+// ------------------------------------------------------------------ bulk TMA copy shared -> global (non-tensor form)
+// Completion is tracked per issuing thread with bulk async-groups.  The source must have been made visible to the
+// async proxy (fence.proxy.async after the generic-proxy stores, before the barrier that hands the buffer over).
+__device__ __forceinline__ void tma_bulk_s2g(void* gdst, uint32_t smem_src_sa, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src_sa), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source (the buffer may be overwritten)
+__device__ __forceinline__ void tma_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk groups of this thread are complete (writes performed)
+__device__ __forceinline__ void tma_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------ TMEM
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {

@@ -37,7 +37,10 @@ constexpr int N_EPI_WARPS = 4 * NPART;
 constexpr int N_EPI_THREADS = N_EPI_WARPS * 32;
 constexpr int EPI_WARP0 = 2;
 constexpr int N_THREADS = EPI_WARP0 * 32 + N_EPI_THREADS;
+constexpr int STORE_WARP = EPI_WARP0 + N_EPI_WARPS;  // training launches only: plane-dump warp (bulk smem -> global)
+constexpr int N_THREADS_DUMP = N_THREADS + 32;
 constexpr int TILE_PTS_T = TILE_ROWS / 4;  // points per tile in tangent mode
+constexpr int CHUNK_PLANE_BYTES = SLOT_HALF_BYTES;  // one dumped chunk half: [8 k-groups][128 rows][8 fp16] = 16 KiB
 
 // dynamic shared memory carve-up (byte offsets from the 1024-aligned base)
 constexpr int SM_A_OFF = 0;
@@ -213,9 +216,12 @@ __device__ __forceinline__ void release_d(const Epi& c, uint32_t g_layer) {
 }
 // Claim the next A ring slot.  Every layer starts after the previous layer's accumulator is complete, i.e. after every
 // earlier MMA has read its A slot: the first NSLOT chunks of a layer never have to wait for a free slot.
+// In training launches (DUMP) the plane-dump warp reads the slots as well and dump-only chunks are interleaved, so
+// the wait is unconditional there.
+template <bool DUMP>
 __device__ __forceinline__ uint32_t claim_slot(const Epi& c, int ck) {
   const uint32_t slot = c.ac % NSLOT;
-  if (ck >= NSLOT) mbar_wait_sa(c.sm + BAR_A_EMPTY + 8 * slot, ((c.ac / NSLOT) & 1) ^ 1, c.err, 400);
+  if (DUMP || ck >= NSLOT) mbar_wait_sa(c.sm + BAR_A_EMPTY + 8 * slot, ((c.ac / NSLOT) & 1) ^ 1, c.err, 400);
   return slot;
 }
 // Hand a finished A-operand chunk to the MMA warp: make the generic-proxy stores visible to the async proxy, then one
@@ -228,34 +234,26 @@ __device__ __forceinline__ void publish_chunk(Epi& c, uint32_t slot, int code) {
 }
 
 // ------------------------------------------------------------------------------------------------ row-form stores
-// Split v[PCOLS] into fp16 hi/lo.  SLOT: store as this row's 16-byte units of k-groups 2 part, 2 part + 1 of an A ring
-// slot (sa = slot base + 2 part A_LBO + 16 row).  DUMP: the same halves to global planes (pointers at this row's
-// first column of the part; training stash / zbar).
-template <bool SLOT, bool DUMP>
-__device__ __forceinline__ void emit_row(uint32_t sa, const float (&v)[PCOLS], uint16_t* dhi, uint16_t* dlo,
-                                         bool dump_lo = true) {
+// Split v[PCOLS] into fp16 hi/lo and store them as this row's 16-byte units of k-groups 2 part, 2 part + 1 of an A
+// ring slot (sa = slot base + 2 part A_LBO + 16 row).
+__device__ __forceinline__ void emit_row(uint32_t sa, const float (&v)[PCOLS]) {
   static_for<0, PCOLS / 8>([&](auto gc) {
     constexpr int g = decltype(gc)::value;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], hi[j], lo[j]);
-    if constexpr (SLOT) {
-      sts128<g * A_LBO>(sa, hi[0], hi[1], hi[2], hi[3]);
-      sts128<g * A_LBO + SLOT_HALF_BYTES>(sa, lo[0], lo[1], lo[2], lo[3]);
-    }
-    if constexpr (DUMP) {
-      *reinterpret_cast<uint4*>(dhi + 8 * g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      if (dump_lo) *reinterpret_cast<uint4*>(dlo + 8 * g) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
+    sts128<g * A_LBO>(sa, hi[0], hi[1], hi[2], hi[3]);
+    sts128<g * A_LBO + SLOT_HALF_BYTES>(sa, lo[0], lo[1], lo[2], lo[3]);
   });
 }
 
-// read PCOLS values back from fp16 hi/lo planes (value = hi + lo)
-__device__ __forceinline__ void load_planes(const uint16_t* phi, const uint16_t* plo, float (&h)[PCOLS], bool use_lo) {
+// Read this row's PCOLS values of a dumped plane chunk (value = hi + lo; plo may be null).  phi / plo point at the
+// chunk half + 2 part A_LBO + 16 row, i.e. the layout emit_row wrote into the ring slot.
+__device__ __forceinline__ void load_planes(const uint8_t* phi, const uint8_t* plo, float (&h)[PCOLS]) {
 #pragma unroll
   for (int g = 0; g < PCOLS / 8; ++g) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(phi + 8 * g));
-    const uint4 b = use_lo ? __ldg(reinterpret_cast<const uint4*>(plo + 8 * g)) : make_uint4(0u, 0u, 0u, 0u);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(phi + g * A_LBO));
+    const uint4 b = plo ? __ldg(reinterpret_cast<const uint4*>(plo + g * A_LBO)) : make_uint4(0u, 0u, 0u, 0u);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -263,6 +261,23 @@ __device__ __forceinline__ void load_planes(const uint16_t* phi, const uint16_t*
       const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[j]));
       h[8 * g + 2 * j] = fa.x + fb.x;
       h[8 * g + 2 * j + 1] = fa.y + fb.y;
+    }
+  }
+}
+
+// SRC_PLANE: copy this row's 16-byte units (k-groups 2 part, 2 part + 1; hi and lo halves) of a dumped chunk into the
+// ring slot.  off = 2 part A_LBO + 16 row (the same offset in the chunk and in the slot half).
+__device__ __forceinline__ void copy_plane_row(uint32_t slot_sa, const uint8_t* chi, const uint8_t* clo, uint32_t off) {
+#pragma unroll
+  for (int g = 0; g < PCOLS / 8; ++g) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(chi + off + g * A_LBO));
+    const uint4 b = clo ? __ldg(reinterpret_cast<const uint4*>(clo + off + g * A_LBO)) : make_uint4(0u, 0u, 0u, 0u);
+    if (g == 0) {
+      sts128<0>(slot_sa + off, a.x, a.y, a.z, a.w);
+      sts128<SLOT_HALF_BYTES>(slot_sa + off, b.x, b.y, b.z, b.w);
+    } else {
+      sts128<A_LBO>(slot_sa + off, a.x, a.y, a.z, a.w);
+      sts128<A_LBO + SLOT_HALF_BYTES>(slot_sa + off, b.x, b.y, b.z, b.w);
     }
   }
 }
@@ -295,7 +310,7 @@ static __device__ __noinline__ void encode_chunk(uint32_t slot_sa, int src, int 
     }
   });
   if (src == SRC_COLOR_B && PCOLS * part >= 32) return;
-  emit_row<true, false>(slot_sa + 2 * part * A_LBO + row * 16, v, nullptr, nullptr);
+  emit_row(slot_sa + 2 * part * A_LBO + row * 16, v);
 }
 
 // =================================================================================================================
@@ -303,20 +318,21 @@ static __device__ __noinline__ void encode_chunk(uint32_t slot_sa, int src, int 
 // =================================================================================================================
 
 // sum a per-row float4 across the NPART column-part threads of the row (every one of them gets the total)
-__device__ __forceinline__ float4 cross_part_sum(const Epi& c, float4 part) {
+__device__ __forceinline__ float4 cross_part_sum_row(const Epi& c, int row, float4 part) {
   const uint32_t xch = c.sm + SM_XCH_OFF;
-  sts128<0>(xch + (c.part * TILE_ROWS + c.row) * 16, __float_as_uint(part.x), __float_as_uint(part.y),
+  sts128<0>(xch + (c.part * TILE_ROWS + row) * 16, __float_as_uint(part.x), __float_as_uint(part.y),
             __float_as_uint(part.z), __float_as_uint(part.w));
   named_bar_sync(1, N_EPI_THREADS);
-  float4 t = lds128f(xch + c.row * 16);
+  float4 t = lds128f(xch + row * 16);
 #pragma unroll
   for (int q = 1; q < NPART; ++q) {
-    const float4 b = lds128f(xch + (q * TILE_ROWS + c.row) * 16);
+    const float4 b = lds128f(xch + (q * TILE_ROWS + row) * 16);
     t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
   }
   named_bar_sync(2, N_EPI_THREADS);  // everyone has read before the buffer is written again
   return t;
 }
+__device__ __forceinline__ float4 cross_part_sum(const Epi& c, float4 part) { return cross_part_sum_row(c, c.row, part); }
 
 // Read this thread's PCOLS columns of 64-col block `blk` of accumulator buffer `buf`, add bias (row `bias_row` of the
 // smem-staged bias table), activate.
@@ -356,10 +372,10 @@ __device__ __forceinline__ void load_raw(const Epi& c, int buf, int blk, float (
 //   softplus : sigma = 1 - exp(-100 h_primal)    (h = softplus(z)  =>  sigma(100 z) = 1 - exp(-100 h))
 //              tangent rows: zdotbar_j = sigma * u_j
 //              primal row  : zbar = sigma * u + 100 (1 - sigma) * sum_j hdot_j * u_j      (softplus'' = 100 s (1-s))
-__device__ __forceinline__ void bwd_gate_plain(const uint16_t* shi, const uint16_t* slo, int act, bool use_lo,
-                                               float (&u)[PCOLS]) {
+// ghi / glo: the gating chunk's halves at this row's first column of the part (glo may be null: hi only)
+__device__ __forceinline__ void bwd_gate_plain(const uint8_t* ghi, const uint8_t* glo, int act, float (&u)[PCOLS]) {
   float h[PCOLS];
-  load_planes(shi, slo, h, use_lo);
+  load_planes(ghi, glo, h);
   if (act == ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < PCOLS; ++i) u[i] = h[i] > 0.f ? u[i] : 0.f;
@@ -390,10 +406,10 @@ __device__ __forceinline__ void dot_accum(const float (&v)[PCOLS], const float* 
 
 // Consume the whole accumulator of global layer g_layer through a NOUT-wide fp32 output layer (no MMA):
 // out = W_out . act(D + bias) summed over the column parts.  Out of line (once or twice per tile).
-// st_hi / st_lo: training stash planes at this row's column 0, or null.
+// keep: training - the layer's input also goes through the A ring as 4 dump-only chunks (the caller advances c.ac).
 template <int NOUT>
 static __device__ __noinline__ float4 tail_dot(Epi c, uint32_t g_layer, int act, int bias, const float* w_out,
-                                               uint16_t* st_hi, uint16_t* st_lo, bool st_lo_on) {
+                                               bool keep) {
   wait_d_full(c, g_layer);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -401,15 +417,96 @@ static __device__ __noinline__ float4 tail_dot(Epi c, uint32_t g_layer, int act,
     float v[PCOLS];
     load_act_dyn(c, act, g_layer & 1, blk, bias, v);
     const int co = 64 * blk + PCOLS * c.part;
-    if (st_hi) emit_row<false, true>(0, v, st_hi + co, st_lo + co, st_lo_on);
+    if (keep) {
+      const uint32_t slot = claim_slot<true>(c, blk);
+      emit_row(c.sm + SM_A_OFF + slot * SLOT_BYTES + 2 * c.part * A_LBO + c.row * 16, v);
+      publish_chunk(c, slot, 900 + blk);
+      ++c.ac;
+    }
     dot_accum<NOUT>(v, w_out + co, acc);
   }
   release_d(c, g_layer);
   return cross_part_sum(c, make_float4(acc[0], acc[1], acc[2], acc[3]));
 }
 
+// ------------------------------------------------------------------------------------------------ input adjoints
+// Adjoint of the network-input features of one row.  E[i] = d loss / d (column PCOLS*PART + i of encoder chunk SRC of
+// this row); the row is stream rs.s of its point (0 primal, j+1 = d/dx_j tangent row, whose entries are the first
+// derivatives of the features, so its adjoint meets the second derivatives).  Accumulates d loss / d var[0..9]
+// (es_program.h Feat: 0..2 position, 3 time, 4..6 g_c, 7..9 d_c) into xb.
+template <int SRC, int PART>
+__device__ __forceinline__ void inadj_part(const float (&E)[PCOLS], const EncIn& rs, float (&xb)[10]) {
+  float var[10];
+  var[0] = rs.p[0]; var[1] = rs.p[1]; var[2] = rs.p[2];
+  var[3] = rs.t;
+  var[4] = rs.g[0]; var[5] = rs.g[1]; var[6] = rs.g[2];
+  var[7] = rs.dc[0]; var[8] = rs.dc[1]; var[9] = rs.dc[2];
+  float sn[10][10], cs[10][10];
+  static_for<0, PCOLS>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    constexpr Feat f = chunk_feat(SRC, PCOLS * PART + i);
+    if constexpr (f.var >= 0 && f.freq >= 0) {
+      constexpr bool first = (f.is_cos == 0) || !part_has(SRC, PART, f.var, f.freq, 0);
+      if constexpr (first)
+        sincosf(var[f.var] * static_cast<float>(1 << f.freq), &sn[f.var][f.freq], &cs[f.var][f.freq]);
+    }
+  });
+  const int s = rs.s;
+  static_for<0, PCOLS>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    constexpr Feat f = chunk_feat(SRC, PCOLS * PART + i);
+    if constexpr (f.var >= 0) {
+      float d1, d2;
+      if constexpr (f.freq < 0) {
+        d1 = 1.f;
+        d2 = 0.f;
+      } else {
+        constexpr float fr = static_cast<float>(1 << f.freq);
+        d1 = f.is_cos ? -fr * sn[f.var][f.freq] : fr * cs[f.var][f.freq];
+        d2 = f.is_cos ? -(fr * fr) * cs[f.var][f.freq] : -(fr * fr) * sn[f.var][f.freq];
+      }
+      if constexpr (f.var < 3) xb[f.var] += (s == 0) ? E[i] * d1 : ((s - 1 == f.var) ? E[i] * d2 : 0.f);
+      else xb[f.var] += (s == 0) ? E[i] * d1 : 0.f;
+    }
+  });
+}
+
+// Read this row's PCOLS raw accumulator columns of part `part` of 64-col block `blk` (= chunk `src` of the network
+// input) and push them through inadj_part.  Out of line like encode_chunk (sin/cos tables, once per tile).
+static __device__ __noinline__ void inadj_chunk(uint32_t taddr, int src, int part, float p0, float p1, float p2,
+                                                float g0, float g1, float g2, float d0, float d1, float d2, int s,
+                                                float* xb_out) {
+  EncIn e;
+  e.p[0] = p0; e.p[1] = p1; e.p[2] = p2;
+  e.t = 0.f;
+  e.g[0] = g0; e.g[1] = g1; e.g[2] = g2;
+  e.dc[0] = d0; e.dc[1] = d1; e.dc[2] = d2;
+  e.s = s;
+  float E[PCOLS];
+  tmem_ld<PCOLS>(taddr, E);
+  tmem_ld_wait();
+  float xb[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) xb[i] = xb_out[i];
+  static_for<0, NPART>([&](auto pc) {
+    constexpr int P = decltype(pc)::value;
+    if (part == P) {
+      if (src == SRC_ENC_SDF) inadj_part<SRC_ENC_SDF, P>(E, e, xb);
+      else if (src == SRC_COLOR_A) inadj_part<SRC_COLOR_A, P>(E, e, xb);
+      else if constexpr (PCOLS * P < 32) {
+        if (src == SRC_COLOR_B) inadj_part<SRC_COLOR_B, P>(E, e, xb);
+      }
+    }
+  });
+#pragma unroll
+  for (int i = 0; i < 10; ++i) xb_out[i] = xb[i];
+}
+
 template <int CHAIN, bool BWD, bool STASH>
 __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const ChainIO& io, Epi& c, long long n_tiles) {
+  constexpr bool DUMP = BWD || STASH;
+  const float scale = (BWD && io.scale) ? __ldg(io.scale) : 1.f;
+  const uint32_t row_off = 2 * c.part * A_LBO + c.row * 16;  // this thread's 16-byte units inside a chunk half
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ---------------------------------------------------------- row state
     float xc[3] = {0.f, 0.f, 0.f};        // canonical point (after the deform tail / = x without deform)
@@ -418,9 +515,9 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
     const bool valid = p_raw < io.n_points;
     const long long pt = valid ? p_raw : io.n_points - 1;
     if constexpr (BWD) {
-      if (valid) {  // padding rows carry zero adjoints so they add nothing to the weight gradients
+      if (valid && io.adj) {  // padding rows carry zero adjoints so they add nothing to the weight gradients
         const float4 a = __ldg(reinterpret_cast<const float4*>(io.adj) + pt);
-        adj[0] = a.x; adj[1] = a.y; adj[2] = a.z; adj[3] = a.w;
+        adj[0] = a.x * scale; adj[1] = a.y * scale; adj[2] = a.z * scale; adj[3] = a.w * scale;
       }
     } else if constexpr (CHAIN == CHAIN_COLOR) {
 #pragma unroll
@@ -430,7 +527,9 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
       for (int i = 0; i < 3; ++i) xc[i] = __ldg(io.x + pt * 3 + i);
     }
     float sdf_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const size_t row_global = static_cast<size_t>(tile) * TILE_ROWS + c.row;  // stash row
+    const uint8_t* gate_tile = BWD ? io.gate_hi + static_cast<size_t>(tile) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
+    const uint8_t* gate_tile_lo =
+        (BWD && prog.gate_use_lo) ? io.gate_lo + static_cast<size_t>(tile) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
 
     for (int l = 0; l < prog.n_layers; ++l, ++c.g) {
       const LayerProg& L = prog.layer[l];
@@ -442,7 +541,7 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
 
       if (!BWD && L.pre_op == PRE_DEFORM_TAIL) {
         // deform output layer (3 x 256, fp32 FFMA) -> x_c = x + delta
-        float4 r = tail_dot<3>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, nullptr, nullptr, false);
+        float4 r = tail_dot<3>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, false);
         xc[0] += r.x + __ldg(prog.deform_out_b + 0);
         xc[1] += r.y + __ldg(prog.deform_out_b + 1);
         xc[2] += r.z + __ldg(prog.deform_out_b + 2);
@@ -454,9 +553,9 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
       }
 
       for (int ck = 0; ck < n_chunks; ++ck, ++c.ac) {
-        const uint32_t slot = claim_slot(c, ck);
+        const uint32_t slot = claim_slot<DUMP>(c, ck);
         const uint32_t slot_sa = c.sm + SM_A_OFF + slot * SLOT_BYTES;
-        const uint32_t row_sa = slot_sa + 2 * c.part * A_LBO + c.row * 16;
+        const uint32_t row_sa = slot_sa + row_off;
         const int src = L.src[ck];
         const int col0 = 64 * L.arg[ck] + PCOLS * c.part;
         if (BWD && (src == SRC_BWD_PREV || src == SRC_BWD_OUTER3)) {
@@ -478,10 +577,17 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
               v[i] = adj[0] * __ldg(prog.outer3_w + col0 + i) + adj[1] * __ldg(prog.outer3_w + HID + col0 + i) +
                      adj[2] * __ldg(prog.outer3_w + 2 * HID + col0 + i);
           }
-          const size_t so = (static_cast<size_t>(L.stash_slot) * io.stash_rows + row_global) * HID + col0;
-          bwd_gate_plain(io.stash_hi + so, io.stash_lo + so, L.bwd_act, L.gate_lo != 0, v);
-          const size_t zo = (static_cast<size_t>(L.zbar_slot) * io.stash_rows + row_global) * HID + col0;
-          emit_row<true, true>(row_sa, v, io.zbar_hi + zo, io.zbar_lo + zo, L.zbar_lo != 0);
+          const size_t go = static_cast<size_t>(L.gate_base + L.arg[ck]) * CHUNK_PLANE_BYTES + row_off;
+          bwd_gate_plain(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, L.bwd_act, v);
+          emit_row(row_sa, v);
+        } else if (BWD && src == SRC_PLANE) {
+          const uint8_t* chi =
+              io.plane_hi + (static_cast<size_t>(tile) * prog.n_plane + L.arg[ck]) * CHUNK_PLANE_BYTES;
+          const uint8_t* clo = prog.plane_lo[ck] != NO_DUMP
+                                   ? io.plane_lo + (static_cast<size_t>(tile) * prog.n_plane_lo + prog.plane_lo[ck]) *
+                                                       CHUNK_PLANE_BYTES
+                                   : nullptr;
+          copy_plane_row(slot_sa, chi, clo, row_off);
         } else if (src == SRC_PREV) {
           float v[PCOLS];
           if (!prev_waited) {
@@ -492,12 +598,7 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
           if (L.side_dot) dot_accum<1>(v, prog.sdf_out_w + col0, sdf_acc);
           if (ck == last_prev) release_d(c, c.g - 1);
           TRACE_EPI(7000 + l * 16 + ck);  // EPI: values ready (tmem + math done)
-          if constexpr (STASH) {  // training: keep this layer's input for the reverse pass / weight gradients
-            const size_t so = (static_cast<size_t>(l) * io.stash_rows + row_global) * HID + col0;
-            emit_row<true, true>(row_sa, v, io.stash_hi + so, io.stash_lo + so, L.stash_lo != 0);
-          } else {
-            emit_row<true, false>(row_sa, v, nullptr, nullptr);
-          }
+          emit_row(row_sa, v);
         } else if (src == SRC_FEAT) {
           float v[PCOLS];
           const float4* f4 = reinterpret_cast<const float4*>(io.feat + pt * HID + col0);
@@ -506,7 +607,7 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
             float4 f = __ldg(f4 + q);
             v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
           }
-          emit_row<true, false>(row_sa, v, nullptr, nullptr);
+          emit_row(row_sa, v);
         } else if (src == SRC_ENC_DEFORM) {
           const float* xp = io.x + pt * 3;
           encode_chunk<false>(slot_sa, src, c.part, c.row, __ldg(xp), __ldg(xp + 1), __ldg(xp + 2),
@@ -546,31 +647,118 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
     const int last = prog.n_layers - 1;
     const int act_last = prog.layer[last].act;
     if (!BWD && prog.post_op == POST_SDF_TAIL) {
-      float4 r = tail_dot<1>(c, c.g - 1, act_last, last, prog.sdf_out_w, nullptr, nullptr, false);
+      float4 r = tail_dot<1>(c, c.g - 1, act_last, last, prog.sdf_out_w, false);
       if (c.part == 0 && valid && io.out_sdf) io.out_sdf[pt] = r.x + __ldg(prog.sdf_out_b);
     } else if (BWD && prog.post_op == POST_BWD_DUMP) {
+      // adjoint of the first layer's pre-activation: feeds no MMA of this launch, goes out as 4 dump-only chunks
       wait_d_full(c, c.g - 1);
 #pragma unroll 1
-      for (int blk = 0; blk < 4; ++blk) {
+      for (int blk = 0; blk < 4; ++blk, ++c.ac) {
         float v[PCOLS];
-        const int col0 = 64 * blk + PCOLS * c.part;
         load_raw(c, (c.g - 1) & 1, blk, v);
-        const size_t so = (static_cast<size_t>(prog.post_stash_slot) * io.stash_rows + row_global) * HID + col0;
-        bwd_gate_plain(io.stash_hi + so, io.stash_lo + so, prog.post_bwd_act, prog.post_gate_lo != 0, v);
-        const size_t zo = (static_cast<size_t>(prog.post_zbar_slot) * io.stash_rows + row_global) * HID + col0;
-        emit_row<false, true>(0, v, io.zbar_hi + zo, io.zbar_lo + zo, prog.post_zbar_lo != 0);
+        const size_t go = static_cast<size_t>(prog.post_gate_base + blk) * CHUNK_PLANE_BYTES + row_off;
+        bwd_gate_plain(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, prog.post_bwd_act, v);
+        const uint32_t slot = claim_slot<true>(c, blk);
+        emit_row(c.sm + SM_A_OFF + slot * SLOT_BYTES + row_off, v);
+        publish_chunk(c, slot, 950 + blk);
       }
       release_d(c, c.g - 1);
     } else if (!BWD && prog.post_op == POST_COLOR_TAIL) {
-      uint16_t* sh = STASH ? io.stash_hi + (static_cast<size_t>(prog.n_layers) * io.stash_rows + row_global) * HID : nullptr;
-      uint16_t* sl = STASH ? io.stash_lo + (static_cast<size_t>(prog.n_layers) * io.stash_rows + row_global) * HID : nullptr;
-      float4 r = tail_dot<3>(c, c.g - 1, act_last, last, prog.color_out_w, sh, sl, prog.tail_stash_lo != 0);
+      float4 r = tail_dot<3>(c, c.g - 1, act_last, last, prog.color_out_w, STASH);
+      if constexpr (STASH) c.ac += 4;
       if (c.part == 0 && valid) {
         float o[3] = {r.x, r.y, r.z};
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           float z = o[i] + __ldg(prog.color_out_b + i);
           io.out_rgb[pt * 3 + i] = 1.f / (1.f + expf(-z));
+        }
+      }
+    } else if (BWD && prog.post_op == POST_FEAT_BAR) {
+      // d loss / d feat = zbar_0 W_0[:, feat] + zbar_skip W_skip[:, feat] / sqrt 2 (colour net), unscaled again
+      wait_d_full(c, c.g - 1);
+      const float inv = 1.f / scale;
+      float m = 0.f;
+#pragma unroll 1
+      for (int blk = 0; blk < 4; ++blk) {
+        float v[PCOLS];
+        load_raw(c, (c.g - 1) & 1, blk, v);
+#pragma unroll
+        for (int i = 0; i < PCOLS; ++i) {
+          v[i] *= inv;
+          m = fmaxf(m, fabsf(v[i]));
+        }
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(io.feat_bar + pt * HID + 64 * blk + PCOLS * c.part);
+#pragma unroll
+          for (int q = 0; q < PCOLS / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+      release_d(c, c.g - 1);
+      if (!valid) m = 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (c.lane == 0 && io.amax_bits) atomicMax(io.amax_bits, __float_as_uint(m));
+    } else if (BWD && prog.post_op == POST_INADJ_COLOR) {
+      // adjoint of [enc10(x_c), g_c, enc4(d_c)] (accumulator columns 0..95 in the kernel's chunk order) pushed back to
+      // x_c, g_c and, through d_c = normalize(J d) (endosurf.py:684-685), to J
+      wait_d_full(c, c.g - 1);
+      const float inv = 1.f / scale;
+      float xb[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) xb[i] = 0.f;
+      float px[3], gcv[3], dd[3], u[3], dcn[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        px[i] = __ldg(io.x_c + pt * 3 + i);
+        gcv[i] = __ldg(io.g_c + pt * 3 + i);
+        dd[i] = __ldg(io.dirs + (pt / io.dir_div) * io.dir_stride + i);
+      }
+      if (io.jac) {
+        const float* J = io.jac + pt * 9;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          u[i] = __ldg(J + 3 * i) * dd[0] + __ldg(J + 3 * i + 1) * dd[1] + __ldg(J + 3 * i + 2) * dd[2];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) u[i] = dd[i];
+      }
+      const float un = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+      const float nrm = un + 1e-10f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dcn[i] = u[i] / nrm;
+      const uint32_t ta = c.tmem + ((c.g - 1) & 1) * HID;
+      inadj_chunk(ta, SRC_COLOR_A, c.part, px[0], px[1], px[2], gcv[0], gcv[1], gcv[2], dcn[0], dcn[1], dcn[2], 0, xb);
+      if (PCOLS * c.part < 32)
+        inadj_chunk(ta + 64, SRC_COLOR_B, c.part, px[0], px[1], px[2], gcv[0], gcv[1], gcv[2], dcn[0], dcn[1], dcn[2],
+                    0, xb);
+      release_d(c, c.g - 1);
+      const float4 sx = cross_part_sum(c, make_float4(xb[0], xb[1], xb[2], 0.f));
+      const float4 sg = cross_part_sum(c, make_float4(xb[4], xb[5], xb[6], 0.f));
+      const float4 sd = cross_part_sum(c, make_float4(xb[7], xb[8], xb[9], 0.f));
+      if (c.part == 0 && valid) {
+        float4* as = reinterpret_cast<float4*>(io.adj_sdf) + pt * 4;
+        const float gb[3] = {sg.x * inv, sg.y * inv, sg.z * inv};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) as[1 + j].w += gb[j];
+        if (io.adj_deform) {
+          float4* ad = reinterpret_cast<float4*>(io.adj_deform) + pt * 4;
+          ad[0].x += sx.x * inv;
+          ad[0].y += sx.y * inv;
+          ad[0].z += sx.z * inv;
+          // d_c = u / (|u| + eps):  ubar = dbar / (|u| + eps) - u (u . dbar) / (|u| (|u| + eps)^2);  Jbar[i][j] = ubar_i d_j
+          const float db[3] = {sd.x * inv, sd.y * inv, sd.z * inv};
+          const float udb = u[0] * db[0] + u[1] * db[1] + u[2] * db[2];
+          const float k = udb / (fmaxf(un, 1e-30f) * nrm * nrm);
+          float ub[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ub[i] = db[i] / nrm - u[i] * k;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            ad[1 + j].x += ub[0] * dd[j];
+            ad[1 + j].y += ub[1] * dd[j];
+            ad[1 + j].z += ub[2] * dd[j];
+          }
         }
       }
     }
@@ -626,36 +814,31 @@ __device__ __forceinline__ void act_frag_dyn(int act, uint32_t bias_sa, Frag& F)
   else act_frag<ACT_NONE>(bias_sa, F);
 }
 
-// split to fp16 hi/lo and store.  SLOT: sa = this thread's base inside an A ring slot (k-group 2 part, row 32Q + p,
-// byte 4q).  DUMP: dhi/dlo = global plane pointers at (row of stream 0, col(0)) (training stash / zbar).
-template <bool SLOT, bool DUMP>
-__device__ __forceinline__ void emit_frag(const Frag& F, uint32_t sa, uint16_t* dhi, uint16_t* dlo, bool dump_lo = true) {
+// split to fp16 hi/lo and store into an A ring slot; sa = this thread's base inside the slot (k-group 2 part,
+// row 32Q + p, byte 4q)
+__device__ __forceinline__ void emit_frag(const Frag& F, uint32_t sa) {
   static_for<0, 4>([&](auto sc) {
     constexpr int s = decltype(sc)::value;
     static_for<0, 2>([&](auto jc) {
       constexpr int j = decltype(jc)::value;
       uint32_t hi, lo;
       split2(F.f[s][2 * j], F.f[s][2 * j + 1], hi, lo);
-      if constexpr (SLOT) {
-        sts32<j * A_LBO + s * 128>(sa, hi);
-        sts32<SLOT_HALF_BYTES + j * A_LBO + s * 128>(sa, lo);
-      }
-      if constexpr (DUMP) {
-        *reinterpret_cast<uint32_t*>(dhi + s * 8 * HID + 8 * j) = hi;
-        if (dump_lo) *reinterpret_cast<uint32_t*>(dlo + s * 8 * HID + 8 * j) = lo;
-      }
+      sts32<j * A_LBO + s * 128>(sa, hi);
+      sts32<SLOT_HALF_BYTES + j * A_LBO + s * 128>(sa, lo);
     });
   });
 }
 
-// fragment of fp16 hi/lo planes (value = hi + lo); pointers at (row of stream 0, col(0))
-__device__ __forceinline__ void load_planes_frag(const uint16_t* phi, const uint16_t* plo, Frag& H, bool use_lo) {
+// fragment of a dumped plane chunk (value = hi + lo, plo may be null); pointers at the chunk half + the same
+// per-thread offset as in the ring slot (k-group 2 part, row 32Q + p, byte 4q).  A warp-wide 4-byte load covers 8
+// consecutive rows x 16 bytes = one full 128-byte line.
+__device__ __forceinline__ void load_planes_frag(const uint8_t* phi, const uint8_t* plo, Frag& H) {
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(phi + s * 8 * HID + 8 * j));
-      const uint32_t b = use_lo ? __ldg(reinterpret_cast<const uint32_t*>(plo + s * 8 * HID + 8 * j)) : 0u;
+      const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(phi + j * A_LBO + s * 128));
+      const uint32_t b = plo ? __ldg(reinterpret_cast<const uint32_t*>(plo + j * A_LBO + s * 128)) : 0u;
       const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&a));
       const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&b));
       H.f[s][2 * j] = fa.x + fb.x;
@@ -665,9 +848,9 @@ __device__ __forceinline__ void load_planes_frag(const uint16_t* phi, const uint
 }
 
 // activation backward on a fragment (see bwd_gate_plain for the formulas); everything is thread-local
-__device__ __forceinline__ void bwd_gate_frag(const uint16_t* shi, const uint16_t* slo, int act, bool use_lo, Frag& U) {
+__device__ __forceinline__ void bwd_gate_frag(const uint8_t* ghi, const uint8_t* glo, int act, Frag& U) {
   Frag H;
-  load_planes_frag(shi, slo, H, use_lo);
+  load_planes_frag(ghi, glo, H);
   if (act == ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -735,10 +918,11 @@ __device__ __forceinline__ void point_sum(const Epi& c, float (&v)[NV]) {
 }
 
 // Consume the whole accumulator of layer g_layer through a NOUT-wide fp32 output layer: out[s * NOUT + o] for the 4
-// streams.  st_hi / st_lo: training stash planes at (row of stream 0, column 0), or null.  Out of line.
+// streams.  keep: training - the layer's input also goes through the A ring as 4 dump-only chunks (the caller
+// advances c.ac); frag_off = this thread's fragment offset inside a ring slot.  Out of line.
 template <int NOUT>
 static __device__ __noinline__ void tail_frag(Epi c, uint32_t g_layer, int act, int bias, const float* w_out,
-                                              uint16_t* st_hi, uint16_t* st_lo, bool st_lo_on, float* out) {
+                                              bool keep, uint32_t frag_off, float* out) {
   wait_d_full(c, g_layer);
   float acc[4][NOUT];
 #pragma unroll
@@ -751,7 +935,12 @@ static __device__ __noinline__ void tail_frag(Epi c, uint32_t g_layer, int act, 
     Frag F;
     load_frag(c.tmem + (g_layer & 1) * HID + 64 * blk, F);
     act_frag_dyn(act, c.sm + SM_BIAS_OFF + (bias * HID + 64 * blk + colq) * 4, F);
-    if (st_hi) emit_frag<false, true>(F, 0, st_hi + 64 * blk + colq, st_lo + 64 * blk + colq, st_lo_on);
+    if (keep) {
+      const uint32_t slot = claim_slot<true>(c, blk);
+      emit_frag(F, c.sm + SM_A_OFF + slot * SLOT_BYTES + frag_off);
+      publish_chunk(c, slot, 900 + blk);
+      ++c.ac;
+    }
     dot_frag<NOUT>(F, w_out + 64 * blk + colq, acc);
   }
   release_d(c, g_layer);
@@ -767,11 +956,13 @@ static __device__ __noinline__ void tail_frag(Epi c, uint32_t g_layer, int act, 
 
 template <bool BWD, bool STASH>
 __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const ChainIO& io, Epi& c, long long n_tiles) {
+  constexpr bool DUMP = BWD || STASH;
   const int q = c.lane & 3, p = c.lane >> 2;
   const int colq = PCOLS * c.part + 2 * q;                                        // col(0) inside a 64-column block
   const uint32_t frag_off = 2 * c.part * A_LBO + (32 * c.quad + p) * 16 + 4 * q;  // see emit_frag
   const uint32_t bias_sa0 = c.sm + SM_BIAS_OFF + colq * 4;
   const bool writer = (c.part == 0);
+  const float scale = (BWD && io.scale) ? __ldg(io.scale) : 1.f;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ---------------------------------------------------------- point state (same for the 4 lanes of a quad)
@@ -784,8 +975,9 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
       for (int i = 0; i < 3; ++i) xc[i] = __ldg(io.x + pt * 3 + i);
     }
     float sdf_acc[4][1] = {{0.f}, {0.f}, {0.f}, {0.f}};
-    // global plane row of stream 0 of this point (stream s: + 8 s rows)
-    const size_t row0 = static_cast<size_t>(tile) * TILE_ROWS + 32 * c.quad + p;
+    const uint8_t* gate_tile = BWD ? io.gate_hi + static_cast<size_t>(tile) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
+    const uint8_t* gate_tile_lo =
+        (BWD && prog.gate_use_lo) ? io.gate_lo + static_cast<size_t>(tile) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
 
     for (int l = 0; l < prog.n_layers; ++l, ++c.g) {
       const LayerProg& L = prog.layer[l];
@@ -798,11 +990,10 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
 
       if (!BWD && L.pre_op == PRE_DEFORM_TAIL) {
         // deform output layer (3 x 256, fp32 FFMA) -> x_c = x + delta ; tangent streams give dDelta/dx_{s-1}
-        // training: the output layer's input goes to stash slot l (this layer has no SRC_PREV chunk of its own)
-        uint16_t* sh = STASH ? io.stash_hi + (static_cast<size_t>(l) * io.stash_rows + row0) * HID : nullptr;
-        uint16_t* sl = STASH ? io.stash_lo + (static_cast<size_t>(l) * io.stash_rows + row0) * HID : nullptr;
+        // training: the output layer's input leaves as 4 dump-only chunks (this layer has no SRC_PREV chunk of its own)
         float o[12];
-        tail_frag<3>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, sh, sl, prog.tail_stash_lo != 0, o);
+        tail_frag<3>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, STASH, frag_off, o);
+        if constexpr (STASH) c.ac += 4;
 #pragma unroll
         for (int i = 0; i < 3; ++i) xc[i] += o[i] + __ldg(prog.deform_out_b + i);
         if (writer && valid) {
@@ -824,7 +1015,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
       }
 
       for (int ck = 0; ck < n_chunks; ++ck, ++c.ac) {
-        const uint32_t slot = claim_slot(c, ck);
+        const uint32_t slot = claim_slot<DUMP>(c, ck);
         const uint32_t slot_sa = c.sm + SM_A_OFF + slot * SLOT_BYTES;
         const int src = L.src[ck];
         const int blk = L.arg[ck];
@@ -840,12 +1031,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
             if (side_dot) dot_frag<1>(F, prog.sdf_out_w + 64 * blk + colq, sdf_acc);
             if (ck == last_prev) release_d(c, c.g - 1);
             TRACE_EPI(7000 + l * 16 + ck);  // EPI: values ready (tmem + math done)
-            if constexpr (STASH) {  // training: keep this layer's input for the reverse pass / weight gradients
-              const size_t so = (static_cast<size_t>(l) * io.stash_rows + row0) * HID + 64 * blk + colq;
-              emit_frag<true, true>(F, slot_sa + frag_off, io.stash_hi + so, io.stash_lo + so, L.stash_lo != 0);
-            } else {
-              emit_frag<true, false>(F, slot_sa + frag_off, nullptr, nullptr);
-            }
+            emit_frag(F, slot_sa + frag_off);
           } else {
             // positional encodings: row-wise, this thread is row 32Q + 8q + p (stream q of its point)
             if (src == SRC_ENC_DEFORM) {
@@ -858,7 +1044,14 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
           }
         } else {
           Frag F;
-          if (src == SRC_ADJ_FEAT) {
+          if (src == SRC_PLANE) {
+            const uint8_t* chi = io.plane_hi + (static_cast<size_t>(tile) * prog.n_plane + blk) * CHUNK_PLANE_BYTES;
+            const uint8_t* clo = prog.plane_lo[ck] != NO_DUMP
+                                     ? io.plane_lo + (static_cast<size_t>(tile) * prog.n_plane_lo + prog.plane_lo[ck]) *
+                                                         CHUNK_PLANE_BYTES
+                                     : nullptr;
+            copy_plane_row(slot_sa, chi, clo, 2 * c.part * A_LBO + c.row * 16);
+          } else if (src == SRC_ADJ_FEAT) {
 #pragma unroll
             for (int s = 0; s < 4; ++s)
 #pragma unroll
@@ -867,9 +1060,9 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
               const float* fp = io.adj_feat + pt * HID + 64 * blk + colq;
               const float2 f0 = __ldg(reinterpret_cast<const float2*>(fp));
               const float2 f1 = __ldg(reinterpret_cast<const float2*>(fp + 8));
-              F.f[0][0] = f0.x; F.f[0][1] = f0.y; F.f[0][2] = f1.x; F.f[0][3] = f1.y;
+              F.f[0][0] = f0.x * scale; F.f[0][1] = f0.y * scale; F.f[0][2] = f1.x * scale; F.f[0][3] = f1.y * scale;
             }
-            emit_frag<true, false>(F, slot_sa + frag_off, nullptr, nullptr);
+            emit_frag(F, slot_sa + frag_off);
           } else {
             if (src == SRC_BWD_PREV) {
               if (!prev_waited) {
@@ -883,7 +1076,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
                 const float2 w1 = __ldg(reinterpret_cast<const float2*>(prog.sdf_out_w + 64 * blk + colq + 8));
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                  const float aw = valid ? __ldg(io.adj + (pt * 4 + s) * 4 + 3) : 0.f;
+                  const float aw = valid ? __ldg(io.adj + (pt * 4 + s) * 4 + 3) * scale : 0.f;
                   F.f[s][0] = fmaf(aw, w0.x, F.f[s][0]);
                   F.f[s][1] = fmaf(aw, w0.y, F.f[s][1]);
                   F.f[s][2] = fmaf(aw, w1.x, F.f[s][2]);
@@ -904,13 +1097,12 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
                 const float4 a = valid ? __ldg(reinterpret_cast<const float4*>(io.adj) + pt * 4 + s)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) F.f[s][i] = a.x * w[0][i] + a.y * w[1][i] + a.z * w[2][i];
+                for (int i = 0; i < 4; ++i) F.f[s][i] = (a.x * w[0][i] + a.y * w[1][i] + a.z * w[2][i]) * scale;
               }
             }
-            const size_t so = (static_cast<size_t>(L.stash_slot) * io.stash_rows + row0) * HID + 64 * blk + colq;
-            bwd_gate_frag(io.stash_hi + so, io.stash_lo + so, L.bwd_act, L.gate_lo != 0, F);
-            const size_t zo = (static_cast<size_t>(L.zbar_slot) * io.stash_rows + row0) * HID + 64 * blk + colq;
-            emit_frag<true, true>(F, slot_sa + frag_off, io.zbar_hi + zo, io.zbar_lo + zo, L.zbar_lo != 0);
+            const size_t go = static_cast<size_t>(L.gate_base + blk) * CHUNK_PLANE_BYTES + frag_off;
+            bwd_gate_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, L.bwd_act, F);
+            emit_frag(F, slot_sa + frag_off);
           }
         }
         publish_chunk(c, slot, l * 16 + ck);
@@ -934,7 +1126,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
     const int last = prog.n_layers - 1;
     if (!BWD && prog.post_op == POST_SDF_TAIL) {
       float o[4];
-      tail_frag<1>(c, c.g - 1, prog.layer[last].act, last, prog.sdf_out_w, nullptr, nullptr, false, o);
+      tail_frag<1>(c, c.g - 1, prog.layer[last].act, last, prog.sdf_out_w, false, frag_off, o);
       if (writer && valid) {
         if (q == 0) {
           if (io.out_sdf) io.out_sdf[pt] = o[0] + __ldg(prog.sdf_out_b);
@@ -943,15 +1135,17 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
         }
       }
     } else if (BWD && prog.post_op == POST_BWD_DUMP) {
+      // adjoint of the first layer's pre-activation: feeds no MMA of this launch, goes out as 4 dump-only chunks
       wait_d_full(c, c.g - 1);
 #pragma unroll 1
-      for (int blk = 0; blk < 4; ++blk) {
+      for (int blk = 0; blk < 4; ++blk, ++c.ac) {
         Frag F;
         load_frag(c.tmem + ((c.g - 1) & 1) * HID + 64 * blk, F);
-        const size_t so = (static_cast<size_t>(prog.post_stash_slot) * io.stash_rows + row0) * HID + 64 * blk + colq;
-        bwd_gate_frag(io.stash_hi + so, io.stash_lo + so, prog.post_bwd_act, prog.post_gate_lo != 0, F);
-        const size_t zo = (static_cast<size_t>(prog.post_zbar_slot) * io.stash_rows + row0) * HID + 64 * blk + colq;
-        emit_frag<false, true>(F, 0, io.zbar_hi + zo, io.zbar_lo + zo, prog.post_zbar_lo != 0);
+        const size_t go = static_cast<size_t>(prog.post_gate_base + blk) * CHUNK_PLANE_BYTES + frag_off;
+        bwd_gate_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, prog.post_bwd_act, F);
+        const uint32_t slot = claim_slot<true>(c, blk);
+        emit_frag(F, c.sm + SM_A_OFF + slot * SLOT_BYTES + frag_off);
+        publish_chunk(c, slot, 950 + blk);
       }
       release_d(c, c.g - 1);
     } else if (!BWD && prog.post_op == POST_FEAT_OUT) {
@@ -970,14 +1164,55 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
         }
       }
       release_d(c, c.g - 1);
+    } else if (BWD && prog.post_op == POST_INADJ_SDF) {
+      // adjoint of the enc6(x_c) rows (accumulator columns 0..63 in the kernel's chunk order; primal + tangent rows)
+      // pushed back to x_c.  Row form: this thread is TMEM lane 32Q + lane = stream lane>>3 of point lane&7.
+      wait_d_full(c, c.g - 1);
+      const int s_row = c.lane >> 3;
+      const long long pr = tile * TILE_PTS_T + 8 * c.quad + (c.lane & 7);
+      const bool vr = pr < io.n_points;
+      const long long ptr_ = vr ? pr : io.n_points - 1;
+      float xb[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) xb[i] = 0.f;
+      inadj_chunk(c.tmem + ((c.g - 1) & 1) * HID, SRC_ENC_SDF, c.part, __ldg(io.x_c + ptr_ * 3),
+                  __ldg(io.x_c + ptr_ * 3 + 1), __ldg(io.x_c + ptr_ * 3 + 2), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, s_row, xb);
+      release_d(c, c.g - 1);
+      // sum over the 4 stream rows of the point (lanes p, p + 8, p + 16, p + 24), then over the column parts
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        xb[i] += __shfl_xor_sync(0xffffffffu, xb[i], 8);
+        xb[i] += __shfl_xor_sync(0xffffffffu, xb[i], 16);
+      }
+      const float4 sx = cross_part_sum_row(c, 32 * c.quad + c.lane, make_float4(xb[0], xb[1], xb[2], 0.f));
+      if (writer && vr && s_row == 0 && io.adj_deform) {
+        const float inv = 1.f / scale;
+        float4* ad = reinterpret_cast<float4*>(io.adj_deform) + ptr_ * 4;
+        ad[0].x += sx.x * inv;
+        ad[0].y += sx.y * inv;
+        ad[0].z += sx.z * inv;
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// dump-only chunk groups of a layer / of the tile end (see ChainProg::pre_dump / post_dump)
+template <bool BWD, bool STASH>
+__device__ __forceinline__ int pre_dump_chunks(const LayerProg& L) {
+  return (!BWD && STASH && L.pre_op == PRE_DEFORM_TAIL) ? 4 : 0;
+}
+template <bool BWD, bool STASH>
+__device__ __forceinline__ int post_dump_chunks(const ChainProg& prog) {
+  if (BWD) return prog.post_op == POST_BWD_DUMP ? 4 : 0;
+  return (STASH && prog.post_op == POST_COLOR_TAIL) ? 4 : 0;
+}
+
 template <int CHAIN, bool TANGENT, bool BWD, bool STASH>
-__global__ void __launch_bounds__(N_THREADS, 1)
+__global__ void __launch_bounds__((BWD || STASH) ? N_THREADS_DUMP : N_THREADS, 1)
 mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__ ChainIO io) {
+  constexpr bool DUMP = BWD || STASH;
+  constexpr int NT = DUMP ? N_THREADS_DUMP : N_THREADS;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -987,7 +1222,8 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_A_FULL) + i, N_EPI_WARPS);  // one elected arrive per epilogue warp
-      mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_A_EMPTY) + i, 1);
+      // slot free = the MMAs that read it have completed (+ the plane-dump warp has read it, training launches)
+      mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_A_EMPTY) + i, DUMP ? 2 : 1);
     }
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_W_FULL) + i, 1);
@@ -1002,8 +1238,8 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   if constexpr (!BWD) {  // stage every layer's bias (+ the feature-layer bias in row MAXL) in shared memory
     float* bs = reinterpret_cast<float*>(smem + SM_BIAS_OFF);
-    for (int i = threadIdx.x; i < prog.n_layers * HID; i += N_THREADS) bs[i] = __ldg(prog.bias + i);
-    for (int i = threadIdx.x; i < HID; i += N_THREADS) bs[MAXL * HID + i] = __ldg(prog.feat_out_b + i);
+    for (int i = threadIdx.x; i < prog.n_layers * HID; i += NT) bs[i] = __ldg(prog.bias + i);
+    for (int i = threadIdx.x; i < HID; i += NT) bs[MAXL * HID + i] = __ldg(prog.feat_out_b + i);
   }
   tc_fence_before();
   __syncthreads();
@@ -1019,6 +1255,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       // ============================================================== TMA producer
       uint32_t wc = 0;
       const int step = (prog.n_terms == 3) ? 1 : 2;  // single-term mode skips the lo units (odd indices)
+      const uint32_t ubytes = static_cast<uint32_t>(prog.unit_bytes);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int u = 0; u < prog.units_per_tile; u += step) {
           const uint32_t st = wc % NSTAGE;
@@ -1027,9 +1264,9 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           if (ES_FLAG(io, 1) && wc >= NSTAGE) {
             mbar_arrive(full);
           } else {
-            mbar_arrive_expect_tx(full, UNIT_BYTES);
-            tma_bulk_g2s(smem + SM_W_OFF + st * UNIT_BYTES, prog.w_units + static_cast<size_t>(u) * UNIT_BYTES,
-                         UNIT_BYTES, full);
+            mbar_arrive_expect_tx(full, ubytes);
+            tma_bulk_g2s(smem + SM_W_OFF + st * UNIT_BYTES, prog.w_units + static_cast<size_t>(u) * ubytes, ubytes,
+                         full);
           }
           ++wc;
         }
@@ -1042,18 +1279,19 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       // The WHOLE warp walks the loop, so every value is warp-uniform and lives in uniform registers - no
       // elect/R2UR broadcast sequence in front of each UTCHMMA - and one elected lane issues.  Ring positions are
       // wrapped counters, not divisions.
-      constexpr uint32_t idesc = make_idesc_f16(TILE_ROWS, HID);
+      const uint32_t idesc = make_idesc_f16(TILE_ROWS, prog.n_mma);
 #ifdef ES_TRACE
       unsigned tcount = 0;
 #endif
       // descriptors as low words (address field in 16-byte units + LBO); the high words are compile-time constants
       constexpr uint32_t A_HI32 = smem_desc_hi(A_SBO), W_HI32 = smem_desc_hi(B_SBO);
+      const uint32_t b_lbo = static_cast<uint32_t>(prog.n_mma) * 16;  // bytes between K core matrices of a weight unit
       const uint32_t a_desc0 = smem_desc_lo(sm + SM_A_OFF, A_LBO);
-      const uint32_t w_desc0 = smem_desc_lo(sm + SM_W_OFF, B_LBO);
+      const uint32_t w_desc0 = smem_desc_lo(sm + SM_W_OFF, b_lbo);
       constexpr uint32_t A_KS = (2 * A_LBO) >> 4;          // one K=16 step inside a slot plane
       constexpr uint32_t A_LO = SLOT_HALF_BYTES >> 4;      // hi plane -> lo plane
       constexpr uint32_t A_SB = (4 * A_LBO) >> 4;          // one 32-wide sub-block
-      constexpr uint32_t W_KS = (2 * B_LBO) >> 4;
+      const uint32_t W_KS = (2 * b_lbo) >> 4;
       static_assert(((SM_W_OFF + NSTAGE * UNIT_BYTES) >> 4) < 0x4000, "descriptor address field");
       const bool three = prog.n_terms == 3;
       const bool do_mma = !ES_FLAG(io, 4);
@@ -1061,10 +1299,19 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       uint32_t st = 0, w_par = 0;      // weight ring stage and its phase parity
       uint32_t slot = 0, a_par = 0;    // A ring slot and its phase parity
       uint32_t g = 0;                  // global layer counter (accumulator buffer g & 1)
+      // dump-only chunks (training): nothing to multiply, only the slot hand-shake
+      auto skip_chunks = [&](int n) {
+        for (int i = 0; i < n; ++i) {
+          mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 311);
+          if (leader) mbar_arrive_sa(sm + BAR_A_EMPTY + 8 * slot);
+          if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
+        }
+      };
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < prog.n_layers; ++l, ++g) {
           const LayerProg& L = prog.layer[l];
           const int n_chunks = L.n_chunks;
+          if constexpr (DUMP) skip_chunks(pre_dump_chunks<BWD, STASH>(L));
           const uint32_t d_tmem = tmem_base + (g & 1) * HID;
           mbar_wait_sa(sm + BAR_D_EMPTY + 8 * (g & 1), ((g >> 1) & 1) ^ 1, err, 300);
           tc_fence_after();
@@ -1115,8 +1362,53 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           if (leader) umma_commit_sa(sm + BAR_D_FULL + 8 * (g & 1));
           TRACE_MMA(3000 + l);  // MMA: all MMAs of layer l issued
         }
+        if constexpr (DUMP) skip_chunks(post_dump_chunks<BWD, STASH>(prog));
       }
       __syncwarp();
+    }
+  } else if (DUMP && warp == STORE_WARP) {
+    // ============================================================== plane-dump warp (training launches)
+    // Walks the same chunk sequence as the epilogue and the MMA warp.  A chunk that is kept leaves as one 16 KiB bulk
+    // copy per half straight out of the ring slot: no epilogue instructions, full-line HBM writes, and the record in
+    // global memory has the ring-slot layout (see LayerProg::dump).
+    if (lane == 0) {
+      uint32_t slot = 0, a_par = 0;
+      auto handle = [&](long long tile, int idx_hi, int idx_lo) {
+        mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 500);
+        const uint32_t slot_sa = sm + SM_A_OFF + slot * SLOT_BYTES;
+        bool any = false;
+        if (idx_hi != NO_DUMP && io.dump_hi) {
+          tma_bulk_s2g(io.dump_hi + (static_cast<size_t>(tile) * prog.n_dump + idx_hi) * CHUNK_PLANE_BYTES, slot_sa,
+                       CHUNK_PLANE_BYTES);
+          any = true;
+        }
+        if (idx_lo != NO_DUMP && io.dump_lo) {
+          tma_bulk_s2g(io.dump_lo + (static_cast<size_t>(tile) * prog.n_dump_lo + idx_lo) * CHUNK_PLANE_BYTES,
+                       slot_sa + SLOT_HALF_BYTES, CHUNK_PLANE_BYTES);
+          any = true;
+        }
+        if (any) {
+          tma_bulk_commit();
+          tma_bulk_wait_read0();
+        }
+        mbar_arrive_sa(sm + BAR_A_EMPTY + 8 * slot);
+        if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
+      };
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < prog.n_layers; ++l) {
+          const LayerProg& L = prog.layer[l];
+          const int npre = pre_dump_chunks<BWD, STASH>(L);
+          for (int i = 0; i < npre; ++i)
+            handle(tile, prog.pre_dump == NO_DUMP ? NO_DUMP : prog.pre_dump + i,
+                   prog.pre_dump_lo == NO_DUMP ? NO_DUMP : prog.pre_dump_lo + i);
+          for (int ck = 0; ck < L.n_chunks; ++ck) handle(tile, L.dump[ck], L.dump_lo[ck]);
+        }
+        const int npost = post_dump_chunks<BWD, STASH>(prog);
+        for (int i = 0; i < npost; ++i)
+          handle(tile, prog.post_dump == NO_DUMP ? NO_DUMP : prog.post_dump + i,
+                 prog.post_dump_lo == NO_DUMP ? NO_DUMP : prog.post_dump_lo + i);
+      }
+      tma_bulk_wait0();
     }
   } else {
     // ============================================================== epilogue warps
@@ -1155,14 +1447,16 @@ static cudaError_t launch_one(const ChainProg& prog, const ChainIO& io, int n_sm
   long long n_tiles = (io.n_points + pts_per_tile - 1) / pts_per_tile;
   if (n_tiles <= 0) return cudaSuccess;
   int grid = static_cast<int>(n_tiles < n_sms ? n_tiles : n_sms);
-  kern<<<grid, N_THREADS, SM_TOTAL, stream>>>(prog, io);
+  kern<<<grid, (BWD || STASH) ? N_THREADS_DUMP : N_THREADS, SM_TOTAL, stream>>>(prog, io);
   return cudaGetLastError();
 }
 
 cudaError_t launch_mlp_chain(int chain, bool tangent, bool use_deform, const ChainProg& prog, const ChainIO& io,
                              int n_sms, cudaStream_t stream, bool bwd) {
   (void)use_deform;  // the layer program already encodes whether a deformation network is present
-  const bool stash = !bwd && io.stash_hi != nullptr;
+  const bool stash = !bwd && io.dump_hi != nullptr;
+  if (prog.n_mma < 16 || prog.n_mma > HID || prog.n_mma % 16 != 0 || prog.unit_bytes != prog.n_mma * SUB_K * 2)
+    return cudaErrorInvalidValue;
   if (chain == CHAIN_COLOR) {
     if (bwd) return launch_one<CHAIN_COLOR, false, true, false>(prog, io, n_sms, stream);
     return stash ? launch_one<CHAIN_COLOR, false, false, true>(prog, io, n_sms, stream)

@@ -49,6 +49,39 @@ __global__ void pack_layer_T_kernel(const float* __restrict__ w, int k_valid, in
   *reinterpret_cast<uint4*>(p + UNIT_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// Input-adjoint operand: B[n][k] = w[k][cols[n]] * scale (k = forward out-feature < k_valid, n < n_mma; cols[n] < 0:
+// zero).  K = 256 (8 sub-blocks of 32); units of n_mma * 64 bytes, [hi(sb0), lo(sb0), hi(sb1), ...], each
+// [k-group 0..3][n][8 fp16] (the K-major layout of the chains' weight units with N = n_mma).
+__global__ void pack_inadj_kernel(const float* __restrict__ w, int k_valid, int n_in_stride,
+                                  const int* __restrict__ cols, int n_mma, float scale, uint8_t* __restrict__ units) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (sb, kg, n)
+  if (idx >= (HID / SUB_K) * 4 * n_mma) return;
+  const int n = idx % n_mma;
+  const int kg = (idx / n_mma) % 4;
+  const int sb = idx / (4 * n_mma);
+  const int col = cols[n];
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = sb * SUB_K + kg * 8 + j;
+    v[j] = (k < k_valid && col >= 0) ? w[static_cast<size_t>(k) * n_in_stride + col] * scale : 0.f;
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+  const size_t ub = static_cast<size_t>(n_mma) * SUB_K * 2;
+  uint8_t* p = units + static_cast<size_t>(2 * sb) * ub + static_cast<size_t>(kg) * n_mma * 16 + n * 16;
+  *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(p + ub) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+cudaError_t launch_pack_inadj(const float* w, int k_valid, int n_in_stride, const int* cols_dev, int n_mma, float scale,
+                              uint8_t* units_out, cudaStream_t stream) {
+  const int total = (HID / SUB_K) * 4 * n_mma;
+  pack_inadj_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, k_valid, n_in_stride, cols_dev, n_mma, scale, units_out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_layer_T(const float* w, int k_valid, int n_in_stride, int n_valid, float scale,
                                 uint8_t* units_out, cudaStream_t stream) {
   const int total = (HID / SUB_K) * 4 * HID;

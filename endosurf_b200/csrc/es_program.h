@@ -42,10 +42,18 @@ enum : uint8_t {
   SRC_ADJ_FEAT,     // d loss / d feat [P,256] (primal rows; tangent rows are zero)
   SRC_BWD_PREV,     // activation-backward of the previous reverse layer's accumulator using the forward stash
   SRC_BWD_OUTER3,   // same, but the incoming adjoint is adj.xyz . W_out (the 3-wide output layer, no MMA)
+  SRC_PLANE,        // copy of a 64-column fp16 hi/lo plane chunk written by an earlier launch (arg = chunk index)
 };
 enum : uint8_t { ACT_NONE = 0, ACT_RELU = 1, ACT_SOFTPLUS100 = 2 };
 enum : uint8_t { PRE_NONE = 0, PRE_DEFORM_TAIL = 1 };
-enum : uint8_t { POST_NONE = 0, POST_SDF_TAIL = 1, POST_FEAT_OUT = 2, POST_COLOR_TAIL = 3, POST_BWD_DUMP = 4 };
+enum : uint8_t {
+  POST_NONE = 0, POST_SDF_TAIL = 1, POST_FEAT_OUT = 2, POST_COLOR_TAIL = 3, POST_BWD_DUMP = 4,
+  // input-adjoint launches of the training backward (one MMA layer whose chunks are SRC_PLANE copies of zbar planes)
+  POST_INADJ_SDF = 5,    // adjoint of enc6(x_c) rows (primal + tangent)      -> d loss / d x_c
+  POST_INADJ_COLOR = 6,  // adjoint of [enc10(x_c), g_c, enc4(d_c)]           -> d loss / d (x_c, g_c, J)
+  POST_FEAT_BAR = 7,     // adjoint of the geometry feature (colour-net input) -> feat_bar [P,256] fp32
+};
+constexpr uint8_t NO_DUMP = 0xFF;
 
 struct LayerProg {
   uint8_t n_chunks;
@@ -57,14 +65,15 @@ struct LayerProg {
   uint8_t arg[MAXC];
   uint8_t nsub[MAXC];  // number of 32-wide K sub-blocks in the chunk that carry weights (1 or 2)
   // reverse chains only
-  uint8_t stash_slot;  // forward stash slot holding the activations whose derivative gates this layer's input
-  uint8_t zbar_slot;   // where this layer's input (adjoint of a forward pre-activation) is dumped for the weight grads
   uint8_t bwd_act;     // activation being differentiated (ACT_RELU / ACT_SOFTPLUS100)
   uint8_t rank1;       // 1: add adj.w * sdf_out_w[col] to the incoming adjoint (sdf row of the output layer)
-  // which fp16 lo planes the training path touches (host: apply_plane_mode; 1 everywhere in full-plane mode)
-  uint8_t stash_lo;    // forward: also write the lo plane of this layer's stash slot
-  uint8_t zbar_lo;     // reverse: also write the lo plane of this layer's zbar slot
-  uint8_t gate_lo;     // reverse: read the lo plane of the stash slot that gates this layer (softplus needs the value)
+  // training planes.  Every A-operand chunk a training launch builds in shared memory can be kept: a dedicated warp
+  // bulk-copies the 16 KiB hi (and optionally lo) half of the ring slot to global memory as is, so a plane chunk in
+  // HBM is [k-group of 8 columns][128 tile rows][8 fp16] - at once the K-major A operand of the chains (SRC_PLANE
+  // reload) and the MN-major operand of the weight-gradient kernel (es_wgrad.cu), both by plain 1-D bulk copies.
+  uint8_t dump[MAXC];     // per chunk: index of the chunk in this launch's hi plane record of a tile (NO_DUMP: none)
+  uint8_t dump_lo[MAXC];  // same for the lo plane record (NO_DUMP: lo half not kept)
+  uint8_t gate_base;      // reverse: chunk index (forward stash record) of column block 0 of the gating activations
 };
 
 // host helper: fill LayerProg::last_prev after the chunk list is complete
@@ -91,9 +100,18 @@ struct ChainProg {
   const float* color_out_b;   // [3]
   const float* outer3_w;      // reverse chains: [3][256] output-layer weights for SRC_BWD_OUTER3
   // POST_BWD_DUMP: last activation-backward of a reverse chain (its result feeds no MMA, only the weight grads)
-  int32_t post_stash_slot, post_zbar_slot, post_bwd_act;
-  int32_t post_zbar_lo, post_gate_lo;  // lo-plane flags of the POST_BWD_DUMP step
-  int32_t tail_stash_lo;               // lo plane of the 3-wide output layers' input stash (deform / colour tails)
+  int32_t post_gate_base, post_bwd_act;
+  // dump-only chunk groups (4 chunks each, no MMA): the inputs of the 3-wide output layers in the forward training
+  // chains (PRE_DEFORM_TAIL / POST_COLOR_TAIL) and the POST_BWD_DUMP result.  First chunk index, NO_DUMP = not kept.
+  uint8_t pre_dump, pre_dump_lo, post_dump, post_dump_lo;
+  int32_t n_dump, n_dump_lo;    // chunks per tile in this launch's hi / lo plane records
+  int32_t n_gate;               // chunks per tile in the forward stash record read by the reverse gates
+  int32_t gate_use_lo;          // gates read hi + lo (the lo record has the same indexing as the hi record)
+  int32_t n_plane, n_plane_lo;  // chunks per tile of the SRC_PLANE source records (lo index = dump_lo of the source)
+  uint8_t plane_lo[MAXC];       // SRC_PLANE: lo-record chunk index of chunk ck of layer 0 (NO_DUMP: lo = 0)
+  // MMA shape of this launch (input-adjoint launches use narrower N)
+  int32_t n_mma;                // UMMA N (256 for the chains)
+  int32_t unit_bytes;           // bytes of one weight unit = n_mma * 32 * 2
 };
 
 // ------------------------------------------------------------------------------------------------------------------

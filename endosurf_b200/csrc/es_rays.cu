@@ -312,8 +312,180 @@ composite_kernel(const float* __restrict__ rays, long long n_rays, const float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ compositing backward
+// Reverse of composite_kernel for the training path (the reference lets autograd differentiate endosurf.py:168-203).
+// One warp per ray.  Inputs: what the forward saw (z, sdf, g_c, J, rgb, variance) and the adjoints of the outputs;
+// outputs: the adjoint rows the three reverse MLP chains start from, and d loss / d inv_s per ray.
+//   w_i = alpha_i T_i, T_i = prod_{k<i} x_k, x_k = 1 - alpha_k + 1e-7:
+//   alpha_bar_i = wbar_i T_i - (sum_{k>i} wbar_k w_k) / x_i            (closed-form cumprod backward, x_k >= 1e-7)
+__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK)
+composite_bwd_kernel(const float* __restrict__ rays, long long n_rays, const float* __restrict__ z_in, int m,
+                     float sample_dist, const float* __restrict__ sdf, const float* __restrict__ g_c,
+                     const float* __restrict__ jac, const float* __restrict__ rgb, const float* __restrict__ variance,
+                     float cos_anneal, CompositeBwd b) {
+  __shared__ float s_al[RAYS_PER_BLOCK][MAX_S];   // alpha
+  __shared__ float s_T[RAYS_PER_BLOCK][MAX_S];    // transmittance before sample i
+  __shared__ float s_w[RAYS_PER_BLOCK][MAX_S];    // weights
+  __shared__ float s_ab[RAYS_PER_BLOCK][MAX_S];   // wbar, then alpha_bar
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * RAYS_PER_BLOCK + w;
+  if (r >= n_rays) return;
+  const Ray R = load_ray(rays, r);
+  const float raw_s = expf(__ldg(variance) * 10.f);
+  const float inv_s = fminf(fmaxf(raw_s, 1e-6f), 1e6f);
+  float* al = s_al[w];
+  float* sT = s_T[w];
+  float* sw = s_w[w];
+  float* sab = s_ab[w];
+  const float* z = z_in + r * m;
+  const float cb[3] = {b.color_bar ? __ldg(b.color_bar + r * 3) : 0.f, b.color_bar ? __ldg(b.color_bar + r * 3 + 1) : 0.f,
+                       b.color_bar ? __ldg(b.color_bar + r * 3 + 2) : 0.f};
+  const float db = b.depth_bar ? __ldg(b.depth_bar + r) : 0.f;
+  const float eb = b.eik_bar ? __ldg(b.eik_bar) / __ldg(b.eik_den) : 0.f;  // d loss / d (sum relax (|g|-1)^2)
+
+  // per-sample forward quantities (same arithmetic as composite_kernel)
+  auto sample = [&](int i, float& dist, float& mid, float (&go)[3], float& tc, float& pc, float& nc, float& e_prev,
+                    float& e_next, float& ratio, float& relax) {
+    const long long p = r * m + i;
+    const float z0 = __ldg(z + i);
+    dist = (i + 1 < m) ? (__ldg(z + i + 1) - z0) : sample_dist;
+    mid = z0 + dist * 0.5f;
+    float pn = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float q = R.o[c] + R.dz[c] * mid;
+      pn += q * q;
+    }
+    relax = sqrtf(pn) < 1.2f ? 1.f : 0.f;
+    const float gc[3] = {__ldg(g_c + p * 3), __ldg(g_c + p * 3 + 1), __ldg(g_c + p * 3 + 2)};
+    if (jac) {
+      const float* J = jac + p * 9;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) go[j] = __ldg(J + j) * gc[0] + __ldg(J + 3 + j) * gc[1] + __ldg(J + 6 + j) * gc[2];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) go[j] = gc[j];
+    }
+    tc = R.d[0] * go[0] + R.d[1] * go[1] + R.d[2] * go[2];
+    const float iter_cos = -(fmaxf(-tc * 0.5f + 0.5f, 0.f) * (1.f - cos_anneal) + fmaxf(-tc, 0.f) * cos_anneal);
+    const float sv = __ldg(sdf + p);
+    e_next = sv + iter_cos * dist * 0.5f;
+    e_prev = sv - iter_cos * dist * 0.5f;
+    pc = sigmoidf_acc(e_prev * inv_s);
+    nc = sigmoidf_acc(e_next * inv_s);
+    ratio = (pc - nc + 1e-6f) / (pc + 1e-6f);
+  };
+
+  for (int i = lane; i < m; i += 32) {
+    float dist, mid, go[3], tc, pc, nc, ep, en, ratio, relax;
+    sample(i, dist, mid, go, tc, pc, nc, ep, en, ratio, relax);
+    al[i] = fminf(fmaxf(ratio, 0.f), 1.f);
+  }
+  __syncwarp();
+  const int seg = (m + 31) / 32;
+  const int b0 = min(lane * seg, m), b1 = min(b0 + seg, m);
+  float prod = 1.f;
+  for (int i = b0; i < b1; ++i) prod *= (1.f - al[i] + 1e-7f);
+  float T = warp_excl_scan<true>(prod, lane);
+  float seg_sum = 0.f;
+  for (int i = b0; i < b1; ++i) {
+    const long long p = r * m + i;
+    const float a = al[i];
+    const float wgt = a * T;
+    sT[i] = T;
+    sw[i] = wgt;
+    T *= (1.f - a + 1e-7f);
+    const float z0 = __ldg(z + i);
+    const float dist = (i + 1 < m) ? (__ldg(z + i + 1) - z0) : sample_dist;
+    float wb = b.weights_bar ? __ldg(b.weights_bar + p) : 0.f;
+    wb += db * (z0 + dist * 0.5f);
+    wb += cb[0] * __ldg(rgb + p * 3) + cb[1] * __ldg(rgb + p * 3 + 1) + cb[2] * __ldg(rgb + p * 3 + 2);
+    sab[i] = wb;
+    seg_sum += wb * wgt;
+  }
+  // suffix sums over lanes: S = sum of wbar_k w_k over all samples after this lane's segment
+  const float total = warp_sum(seg_sum);
+  float S = total - (warp_excl_scan<false>(seg_sum, lane) + seg_sum);
+  for (int i = b1 - 1; i >= b0; --i) {
+    const float wb = sab[i];
+    sab[i] = wb * sT[i] - S / (1.f - al[i] + 1e-7f);
+    S += wb * sw[i];
+  }
+  __syncwarp();
+
+  float invs_bar = 0.f;
+  for (int i = lane; i < m; i += 32) {
+    const long long p = r * m + i;
+    float dist, mid, go[3], tc, pc, nc, ep, en, ratio, relax;
+    sample(i, dist, mid, go, tc, pc, nc, ep, en, ratio, relax);
+    // colour
+    const float wgt = sw[i];
+    float4 oc = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+      const float c0 = __ldg(rgb + p * 3), c1 = __ldg(rgb + p * 3 + 1), c2 = __ldg(rgb + p * 3 + 2);
+      float rb0 = cb[0] * wgt, rb1 = cb[1] * wgt, rb2 = cb[2] * wgt;
+      if (b.rgb_bar) {
+        rb0 += __ldg(b.rgb_bar + p * 3);
+        rb1 += __ldg(b.rgb_bar + p * 3 + 1);
+        rb2 += __ldg(b.rgb_bar + p * 3 + 2);
+      }
+      oc.x = rb0 * c0 * (1.f - c0);  // through the output sigmoid (endosurf.py:841)
+      oc.y = rb1 * c1 * (1.f - c1);
+      oc.z = rb2 * c2 * (1.f - c2);
+    }
+    reinterpret_cast<float4*>(b.adj_color)[p] = oc;
+    // alpha -> cdfs -> sdf, cos
+    const float ratio_bar = (ratio >= 0.f && ratio <= 1.f) ? sab[i] : 0.f;
+    const float den = pc + 1e-6f;
+    float pc_bar = ratio_bar * nc / (den * den);
+    if (b.cdf_bar) pc_bar += __ldg(b.cdf_bar + p);
+    const float nc_bar = -ratio_bar / den;
+    const float ap = pc_bar * pc * (1.f - pc);  // adjoint of (e_prev * inv_s)
+    const float an = nc_bar * nc * (1.f - nc);
+    invs_bar += ap * ep + an * en;
+    const float ep_bar = ap * inv_s, en_bar = an * inv_s;
+    float s_bar = ep_bar + en_bar;
+    if (b.sdf_bar) s_bar += __ldg(b.sdf_bar + p);
+    const float ic_bar = (en_bar - ep_bar) * dist * 0.5f;
+    float tc_bar = 0.f;
+    if (-tc * 0.5f + 0.5f > 0.f) tc_bar += 0.5f * (1.f - cos_anneal) * ic_bar;
+    if (-tc > 0.f) tc_bar += cos_anneal * ic_bar;
+    float gob[3];
+    const float gn = sqrtf(go[0] * go[0] + go[1] * go[1] + go[2] * go[2]);
+    const float ek = (gn > 0.f) ? eb * relax * 2.f * (gn - 1.f) / gn : 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      gob[j] = tc_bar * R.d[j] + ek * go[j];
+      if (b.go_bar) gob[j] += __ldg(b.go_bar + p * 3 + j);
+    }
+    // g_o = J^T g_c:  gc_bar_i = sum_j J[i][j] gobar_j ;  Jbar[i][j] = g_c[i] gobar[j]
+    float4* as = reinterpret_cast<float4*>(b.adj_sdf) + p * 4;
+    as[0] = make_float4(0.f, 0.f, 0.f, s_bar);
+    const float gc[3] = {__ldg(g_c + p * 3), __ldg(g_c + p * 3 + 1), __ldg(g_c + p * 3 + 2)};
+    if (jac) {
+      const float* J = jac + p * 9;
+#pragma unroll
+      for (int i2 = 0; i2 < 3; ++i2)
+        as[1 + i2] = make_float4(0.f, 0.f, 0.f, __ldg(J + 3 * i2) * gob[0] + __ldg(J + 3 * i2 + 1) * gob[1] +
+                                                    __ldg(J + 3 * i2 + 2) * gob[2]);
+      if (b.adj_deform) {
+        float4* ad = reinterpret_cast<float4*>(b.adj_deform) + p * 4;
+        ad[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ad[1 + j] = make_float4(gc[0] * gob[j], gc[1] * gob[j], gc[2] * gob[j], 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int i2 = 0; i2 < 3; ++i2) as[1 + i2] = make_float4(0.f, 0.f, 0.f, gob[i2]);
+    }
+  }
+  invs_bar = warp_sum(invs_bar);
+  if (lane == 0) b.invs_partial[r] = (raw_s >= 1e-6f && raw_s <= 1e6f) ? invs_bar * 10.f * inv_s : 0.f;
+}
+
 // deterministic single-block reduction of the per-ray eikonal partials -> sum(num) / (sum(den) + 1e-6)
-__global__ void eikonal_reduce_kernel(const float* __restrict__ part, long long n_rays, float* __restrict__ out) {
+__global__ void eikonal_reduce_kernel(const float* __restrict__ part, long long n_rays, float* __restrict__ out,
+                                      float* __restrict__ out_den) {
   __shared__ float s_n[32], s_d[32];
   float n = 0.f, d = 0.f;
   for (long long i = threadIdx.x; i < n_rays; i += blockDim.x) {
@@ -332,8 +504,60 @@ __global__ void eikonal_reduce_kernel(const float* __restrict__ part, long long 
     d = threadIdx.x < (blockDim.x >> 5) ? s_d[threadIdx.x] : 0.f;
     n = warp_sum(n);
     d = warp_sum(d);
-    if (threadIdx.x == 0) out[0] = n / (d + 1e-6f);
+    if (threadIdx.x == 0) {
+      out[0] = n / (d + 1e-6f);
+      if (out_den) out_den[0] = d + 1e-6f;
+    }
   }
+}
+// out[0] (+)= sum of part[0..n)   (deterministic, single block)
+__global__ void sum_reduce_kernel(const float* __restrict__ part, long long n, float* __restrict__ out, int accumulate) {
+  __shared__ float s_n[32];
+  float v = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_n[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? s_n[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + v : v;
+  }
+}
+
+// point-field training calls without compositing: the adjoint rows of the reverse chains straight from the
+// adjoints of (sdf, g_c, J, rgb) at explicit points
+__global__ void point_adjoints_kernel(long long n, const float* __restrict__ rgb, const float* __restrict__ sdf_bar,
+                                      const float* __restrict__ gc_bar, const float* __restrict__ jac_bar,
+                                      const float* __restrict__ rgb_bar, float* __restrict__ adj_color,
+                                      float* __restrict__ adj_sdf, float* __restrict__ adj_deform) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  float4 oc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rgb_bar) {
+    const float c0 = rgb[p * 3], c1 = rgb[p * 3 + 1], c2 = rgb[p * 3 + 2];
+    oc.x = rgb_bar[p * 3] * c0 * (1.f - c0);
+    oc.y = rgb_bar[p * 3 + 1] * c1 * (1.f - c1);
+    oc.z = rgb_bar[p * 3 + 2] * c2 * (1.f - c2);
+  }
+  reinterpret_cast<float4*>(adj_color)[p] = oc;
+  float4* as = reinterpret_cast<float4*>(adj_sdf) + p * 4;
+  as[0] = make_float4(0.f, 0.f, 0.f, sdf_bar ? sdf_bar[p] : 0.f);
+  for (int j = 0; j < 3; ++j) as[1 + j] = make_float4(0.f, 0.f, 0.f, gc_bar ? gc_bar[p * 3 + j] : 0.f);
+  if (adj_deform) {
+    float4* ad = reinterpret_cast<float4*>(adj_deform) + p * 4;
+    ad[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 3; ++j)
+      ad[1 + j] = jac_bar ? make_float4(jac_bar[p * 9 + j], jac_bar[p * 9 + 3 + j], jac_bar[p * 9 + 6 + j], 0.f)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void fill_identity_jac_kernel(float* __restrict__ jac, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * 9) return;
+  const int e = static_cast<int>(i % 9);
+  jac[i] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -377,9 +601,35 @@ cudaError_t launch_composite(const RayGeom& rg, const float* z, int m, float sam
       rg.rays, rg.n_rays, z, m, sample_dist, sdf, g_c, jac, rgb, variance, cos_anneal, out);
   return cudaGetLastError();
 }
-cudaError_t launch_eikonal_reduce(const float* eik_partial, long long n_rays, float* out_scalar,
+cudaError_t launch_eikonal_reduce(const float* eik_partial, long long n_rays, float* out_scalar, float* out_den,
                                   cudaStream_t stream) {
-  eikonal_reduce_kernel<<<1, 1024, 0, stream>>>(eik_partial, n_rays, out_scalar);
+  eikonal_reduce_kernel<<<1, 1024, 0, stream>>>(eik_partial, n_rays, out_scalar, out_den);
+  return cudaGetLastError();
+}
+cudaError_t launch_composite_bwd(const RayGeom& rg, const float* z, int m, float sample_dist, const float* sdf,
+                                 const float* g_c, const float* jac, const float* rgb, const float* variance,
+                                 float cos_anneal, const CompositeBwd& b, cudaStream_t stream) {
+  if (rg.n_rays == 0) return cudaSuccess;
+  if (m > MAX_S) return cudaErrorInvalidValue;
+  composite_bwd_kernel<<<blocks_for(rg.n_rays, RAYS_PER_BLOCK), 32 * RAYS_PER_BLOCK, 0, stream>>>(
+      rg.rays, rg.n_rays, z, m, sample_dist, sdf, g_c, jac, rgb, variance, cos_anneal, b);
+  return cudaGetLastError();
+}
+cudaError_t launch_sum_reduce(const float* part, long long n, float* out, int accumulate, cudaStream_t stream) {
+  sum_reduce_kernel<<<1, 1024, 0, stream>>>(part, n, out, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_point_adjoints(long long n, const float* rgb, const float* sdf_bar, const float* gc_bar,
+                                  const float* jac_bar, const float* rgb_bar, float* adj_color, float* adj_sdf,
+                                  float* adj_deform, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  point_adjoints_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(n, rgb, sdf_bar, gc_bar, jac_bar, rgb_bar, adj_color,
+                                                                adj_sdf, adj_deform);
+  return cudaGetLastError();
+}
+cudaError_t launch_fill_identity_jac(float* jac, long long n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  fill_identity_jac_kernel<<<blocks_for(n * 9, 256), 256, 0, stream>>>(jac, n);
   return cudaGetLastError();
 }
 

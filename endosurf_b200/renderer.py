@@ -247,7 +247,8 @@ class EndoSurfRenderer(nn.Module):
         return tuple(p._version for p in self.model.parameters()) + tuple(p.data_ptr() for p in self.model.parameters())
 
     def _sync_weights(self):
-        """Fold weight norm (PyTorch, differentiable plumbing) and repack when any parameter changed."""
+        """Hand the parameters to the library when any of them changed: the weight-norm fold W = g v/|v| (reference
+        utils.py:57-58) and the fp16 hi/lo operand packing both run in the library (es_load_network_wn)."""
         ver = self._params_version()
         if ver == self._packed_version:
             return
@@ -256,18 +257,23 @@ class EndoSurfRenderer(nn.Module):
         if self.model.use_deform:
             nets.append((0, self.model.deform_network))
         nets += [(1, self.model.sdf_network), (2, self.model.color_network)]
-        keep = []
-        with torch.no_grad():
-            for net_id, mod in nets:
-                ws = [l.effective_weight().contiguous() for l in mod.net]
-                bs = [l.bias.detach().contiguous() for l in mod.net]
-                keep += ws + bs
-                wp = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
-                bp = (C.c_void_p * len(bs))(*[b.data_ptr() for b in bs])
-                _lib.check(ctx, lib.es_load_network(ctx, net_id, wp, bp, self._stream()), "es_load_network")
-        self._keepalive = keep  # folded tensors stay alive until the pack kernels have been enqueued and run
+        for net_id, mod in nets:
+            for l in mod.net:
+                for p in (l.weight_v, l.weight_g, l.bias):
+                    if not p.is_contiguous() or p.dtype != torch.float32:
+                        raise ValueError("endosurf_b200 parameters must be contiguous fp32 tensors")
+            n = len(mod.net)
+            vp = (C.c_void_p * n)(*[l.weight_v.data_ptr() for l in mod.net])
+            gp = (C.c_void_p * n)(*[l.weight_g.data_ptr() for l in mod.net])
+            bp = (C.c_void_p * n)(*[l.bias.data_ptr() for l in mod.net])
+            _lib.check(ctx, lib.es_load_network_wn(ctx, net_id, vp, gp, bp, self._stream()), "es_load_network_wn")
         self._packed_version = ver
-        self._loaded_epoch = None
+
+    def _poll_device_error(self):
+        """Non-blocking check of the device-side watchdog word: raises if an EARLIER launch of this context recorded
+        a barrier time-out (results after that are garbage; training must not continue silently)."""
+        lib, ctx = _lib.load(), self._context()
+        _lib.check(ctx, lib.es_poll_error(ctx, self._stream()), "device-side watchdog")
 
     def _const(self, key, fn):
         if key not in self._consts:
@@ -275,22 +281,13 @@ class EndoSurfRenderer(nn.Module):
         return self._consts[key]
 
     # ------------------------------------------------------------------ differentiable (training) path
-    train_ray_chunk = 4096  # rays per autograd.Function call: bounds the activation stash (about 30 GiB per chunk of 4096 x 128 points)
+    train_ray_chunk = 16384  # rays per library call: bounds the plane records (about 4.4 MB per ray at 64+64 samples)
 
-    def point_field(self, x, d, t, wb=None):
+    def point_field(self, x, d, t):
         """Differentiable EndoSurfNet.forward + gradient queries on explicit points:
         (sdf [n,1], g_c [n,3], jac [n,3,3], rgb [n,3]); gradients flow to every network parameter."""
-        from .training import PointFieldFn, effective_weights
-        if wb is None:
-            wb = self.effective_weights()
-        return PointFieldFn.apply(self, wb[0], x, d, t, *wb[1])
-
-    def effective_weights(self):
-        """(epoch, [W_l.., b_l..] per network): fold weight norm once per step; the epoch tags this parameter state
-        so that the CUDA context re-packs its fp16 operand units only when the weights actually changed."""
-        from .training import effective_weights
-        self._wb_epoch = getattr(self, "_wb_epoch", 0) + 1
-        return self._wb_epoch, effective_weights(self.model)
+        from .training import PointFieldFn, param_list
+        return PointFieldFn.apply(self, x, d, t, *param_list(self))
 
     def _sample_z(self, rays, iter_step, perturb_overwrite):
         """Coarse + hierarchical sampling only (no grad, CUDA): z_vals [R,M]."""
@@ -320,41 +317,43 @@ class EndoSurfRenderer(nn.Module):
                    "es_render_rays(sampling)")
         return z
 
-    def _render_rays_train(self, rays, iter_step, perturb_overwrite, z_vals_override=None):
+    def _render_rays_train(self, rays, iter_step, perturb_overwrite, z_vals_override=None, return_extras=False):
         """render_rays with autograd (endosurf.py:60-213): sampling runs without grad exactly as in the reference
-        (:86), the sample-point pipeline is the fused CUDA forward/backward (training.PointFieldFn), compositing
-        is differentiable PyTorch on [R,M] tensors."""
-        from .training import composite
+        (:86); everything after it - points, the three MLPs with normals and Jacobian, compositing - is one fused
+        library forward and one library backward (training.RenderFn)."""
+        from .training import RenderFn, param_list
         rays = rays.detach().contiguous().float()
         R = rays.shape[0]
         with torch.no_grad():
-            z = z_vals_override.detach().float() if z_vals_override is not None else \
+            z = z_vals_override.detach().contiguous().float() if z_vals_override is not None else \
                 self._sample_z(rays, iter_step, perturb_overwrite)
-        M = z.shape[1]
-        sample_dist = 2.0 / self.n_samples
-        rays_o, rays_d, time = rays[:, :3], rays[:, 3:6], rays[:, 8]
-        d_z = rays_d / (rays_d[:, 2:] + 1e-6)
-        dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((R, 1), sample_dist, device=z.device)], -1)
-        mid_z = z + dists * 0.5
-        pts = rays_o[:, None, :] + d_z[:, None, :] * mid_z[..., None]
-        sdf_l, go_l, rgb_l = [], [], []
-        wb = self.effective_weights()
-        for r0 in range(0, R, self.train_ray_chunk):
-            r1 = min(R, r0 + self.train_ray_chunk)
-            n = (r1 - r0) * M
-            x = pts[r0:r1].reshape(n, 3)
-            dd = rays_d[r0:r1, None, :].expand(r1 - r0, M, 3).reshape(n, 3)
-            tt = time[r0:r1, None].expand(r1 - r0, M).reshape(n, 1)
-            sdf, g_c, jac, rgb = self.point_field(x, dd, tt, wb)
-            g_o = (jac * g_c[:, :, None]).sum(1)  # J^T g_c = autograd normal in observed space (SURVEY 7.4)
-            sdf_l.append(sdf.reshape(r1 - r0, M))
-            go_l.append(g_o.reshape(r1 - r0, M, 3))
-            rgb_l.append(rgb.reshape(r1 - r0, M, 3))
-        inv_s = torch.exp(self.model.deviation_network.variance * 10.0).clip(1e-6, 1e6)
-        out = composite(torch.cat(sdf_l), torch.cat(go_l), torch.cat(rgb_l), rays_d, pts, z, sample_dist, inv_s,
-                        self.get_cos_anneal_ratio(iter_step))
-        out["weight_max"] = torch.max(out["weights"], dim=-1, keepdim=True)[0]
-        out["s_val"] = (1.0 / inv_s).expand(R, M).mean(dim=-1, keepdim=True)
+        cos_ratio = self.get_cos_anneal_ratio(iter_step)
+        params = param_list(self)
+        variance = self.model.deviation_network.variance
+        names = ["color_map", "depth_map", "gradients_o", "gradient_o_error", "weights", "cdf", "sdf",
+                 "sampled_color", "weight_max", "s_val"]
+        if R <= self.train_ray_chunk:
+            vals = RenderFn.apply(self, rays, z, cos_ratio, variance, *params)
+            out = dict(zip(names, vals))
+        else:
+            # very large batches: several library calls; the eikonal mean is re-normalised over the whole batch
+            parts = [RenderFn.apply(self, rays[r0:r0 + self.train_ray_chunk], z[r0:r0 + self.train_ray_chunk],
+                                    cos_ratio, variance, *params) for r0 in range(0, R, self.train_ray_chunk)]
+            out = {k: torch.cat([p[i] for p in parts]) for i, k in enumerate(names) if k != "gradient_o_error"}
+            with torch.no_grad():
+                d_z = rays[:, 3:6] / (rays[:, 5:6] + 1e-6)
+                dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((R, 1), 2.0 / self.n_samples, device=z.device)], -1)
+                pts = rays[:, None, :3] + d_z[:, None, :] * (z + dists * 0.5)[..., None]
+                relax = (torch.linalg.norm(pts, dim=-1) < 1.2).float()
+                den = torch.stack([relax[r0:r0 + self.train_ray_chunk].sum() + 1e-6
+                                   for r0 in range(0, R, self.train_ray_chunk)])
+            num = torch.stack([p[3] for p in parts]) * den
+            out["gradient_o_error"] = num.sum() / (relax.sum() + 1e-6)
+        if not return_extras:
+            out.pop("sdf")
+            out.pop("sampled_color")
+        else:
+            out["z_vals"] = z
         return out
 
     # ------------------------------------------------------------------ helper methods of the reference renderer
@@ -533,7 +532,7 @@ class EndoSurfRenderer(nn.Module):
         p = _lib.EsProfile()
         _lib.check(ctx, lib.es_profile_read(ctx, C.byref(p), self._stream()), "es_profile_read")
         names = ["geometry_chain", "color_chain", "sdf_query_chain", "rev_deform_chain", "rev_sdf_chain",
-                 "rev_color_chain"]
+                 "rev_color_chain", "input_adjoint", "wgrad", "wgrad_reduce", "composite", "out_layer_grads"]
         return {n: {"ms": p.ms[i], "launches": int(p.launches[i]), "points": int(p.points[i])}
                 for i, n in enumerate(names)}
 
@@ -595,7 +594,7 @@ class EndoSurfRenderer(nn.Module):
                     return_extras=False, **kwargs):
         """EndoSurfRenderer.render_rays (endosurf.py:60-132): rays [R,9] -> the reference's 8-key dict."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
-            return self._render_rays_train(rays, iter_step, perturb_overwrite, z_vals_override)
+            return self._render_rays_train(rays, iter_step, perturb_overwrite, z_vals_override, return_extras)
         self._sync_weights()
         lib, ctx = _lib.load(), self._context()
         rays = rays.detach().contiguous().float()

@@ -46,6 +46,9 @@ void es_destroy(es_ctx* ctx);
 const char* es_last_error(const es_ctx* ctx);
 /* Synchronises `stream` and returns ES_E_DEVICE if any kernel recorded a device-side error. */
 int es_sync_check(es_ctx* ctx, void* stream);
+/* Non-blocking variant for the production path: enqueues a copy of the error word to pinned host memory and reports
+ * what the PREVIOUS poll delivered, so a tripped watchdog raises at most one call late instead of training on. */
+int es_poll_error(es_ctx* ctx, void* stream);
 int es_num_sms(const es_ctx* ctx);
 
 /* Upload one network's EFFECTIVE weights W_l = g_l * v_l / ||v_l|| (reference utils.py:57-58, folded by the caller)
@@ -68,34 +71,79 @@ int es_point_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div,
                      int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac, float* sdf, float* g_c,
                      float* feat, float* rgb, void* stream);
 
+/* Same as es_load_network but from the reference's parameters themselves (old-API weight norm, utils.py:57-58):
+ * v[l] = weight_v [out_l, in_l], g[l] = weight_g [out_l, 1], b[l] = bias.  The fold W = g v / |v|_row runs on the
+ * device into buffers owned by the context. */
+int es_load_network_wn(es_ctx* ctx, int net, const float* const* v, const float* const* g, const float* const* b,
+                       void* stream);
+
 /* ---- differentiable (training) path -------------------------------------------------------------------------------
- * The reference differentiates EndoSurfNet.forward with torch.autograd (create_graph=True at endosurf.py:594-658 so
- * that the eikonal / colour losses can back-propagate through the normals).  Here the forward keeps, per MMA layer,
- * the layer input of every row (primal + 3 tangent rows per point) as fp16 hi/lo planes ("stash"), and the reverse
- * pass runs the same fused tcgen05 chains on transposed weights, writing the adjoint of every forward
- * pre-activation ("zbar") so that weight gradients are plain [256 x rows] x [rows x 256] GEMMs.
- *   es_train_layout: out6 = {geometry stash rows, geometry stash slots, colour stash rows, colour stash slots,
- *                            zbar slots per reverse chain, geometry slot offset of the sdf layers}.
- *   Planes are uint16 (fp16 bits) [slots][rows][256].  Geometry rows follow the kernels' 128-row tiles of 32 points:
- *   point = 32*tile + 8*Q + p (Q = 0..3, p = 0..7), stream s (0 = primal, 1..3 = d/dx, d/dy, d/dz) of that point is
- *   row 128*tile + 32*Q + 8*s + p (one epilogue thread then owns the four streams of a point through the 16x256b
- *   TMEM fragment loads; endosurf_b200/training.py rows_from_points / points_from_rows convert).  Colour rows =
- *   point.  The adjoint input `adj` of es_point_backward stays indexed by (4*point + stream).                        */
-int es_train_layout(const es_ctx* ctx, int64_t n, int64_t* out6);
-/* Which fp16 lo planes the training launches write/read.  0 (default): only those the 1-term weight-gradient path
- * needs - the sdf stash slots (softplus gating) and the zbar slots of the layers that read the network input;
- * 1: every plane (needed when the caller forms 3-term weight gradients from hi and lo). */
+ * The reference differentiates render_rays with torch.autograd: loss.backward() (trainer_endosurf.py:94-104) runs
+ * through render_core (endosurf.py:168-203), EndoSurfNet.forward and the create_graph=True gradient queries
+ * (endosurf.py:594-658).  Here the forward keeps the input rows of every MMA layer (primal + 3 tangent rows per
+ * point) as fp16 plane records in the caller's `stash` buffer, and the backward is: fused compositing backward ->
+ * three reverse tcgen05 chains on transposed weights (activation gates from the stash, adjoints of every
+ * pre-activation written as plane records) -> input-adjoint launches (adjoints of the positional encodings, g_c,
+ * J d and the geometry feature) -> split-K tcgen05 weight-gradient kernel over the plane records -> weight-norm
+ * backward.  No library GEMMs, no PyTorch ops.
+ *
+ * A plane record is [tile][chunks per tile][16 KiB]; a chunk is 64 columns of a 128-row tile in the kernels' ring
+ * slot layout [k-group of 8 columns][128 rows][8 fp16].  Geometry tiles hold 32 points x 4 streams (row 32Q + 8s + p),
+ * colour tiles 128 points.  es_train_stash_bytes gives the size of `stash` for n points in the current plane mode.
+ * Plane mode 0 (default): fp16 hi planes only (1-term weight gradients, hi-only activation gates) plus the lo halves
+ * the input-adjoint launches need; 1: every lo half as well (3-term weight gradients, exact gates). */
 int es_set_plane_mode(es_ctx* ctx, int32_t full_planes);
-int es_point_forward_train(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
+int es_train_stash_bytes(const es_ctx* ctx, int64_t n, int64_t* out);
+
+/* Parameters and gradient outputs of a backward call; index [net][layer], net = ES_NET_*, tables of n_layers
+ * pointers (the deform tables may be NULL without a deformation network).  v / g: weight_v / weight_g as given to
+ * es_load_network_wn; grad_*: written (not accumulated), same shapes as the parameters. */
+typedef struct es_train_params {
+  const float* const* v[3];
+  const float* const* g[3];
+  float* const* grad_v[3];
+  float* const* grad_g[3];
+  float* const* grad_b[3];
+} es_train_params;
+
+/* EndoSurfNet.forward + gradient queries on explicit points with the stash kept (errorondepth /
+ * surface_neighbour_error during training, endosurf.py:289-342).  Outputs as es_point_forward (all required). */
+int es_point_train_forward(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
                            const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
-                           float* sdf, float* g_c, float* feat, float* rgb, uint16_t* geom_stash_hi,
-                           uint16_t* geom_stash_lo, uint16_t* color_stash_hi, uint16_t* color_stash_lo, void* stream);
-/* Reverse chain of one network (net = ES_NET_*).  adj: [logical rows][4] = adjoint of the row's 3-wide output
- * (deform: d/dDelta on primal rows, d/d(dDelta/dx_j) on tangent rows; colour: d/d(pre-sigmoid rgb)) in xyz and of the
- * sdf-row output in w (sdf chain: d/dsdf on primal rows, d/dg_c[j] on tangent rows).  adj_feat: d/dfeat [n,256]
- * (sdf chain).  zbar planes: [zbar slots][rows][256], slot m = adjoint of forward layer m's pre-activation. */
-int es_point_backward(es_ctx* ctx, int net, int64_t n, const uint16_t* stash_hi, const uint16_t* stash_lo,
-                      const float* adj, const float* adj_feat, uint16_t* zbar_hi, uint16_t* zbar_lo, void* stream);
+                           float* sdf, float* g_c, float* rgb, uint8_t* stash, void* stream);
+/* ... and its reverse: adjoints of sdf [n], g_c [n,3], jac [n,9], rgb [n,3] (any may be NULL = zero) -> parameter
+ * gradients.  x_c, jac, g_c, rgb: the forward's outputs. */
+int es_point_train_backward(es_ctx* ctx, int64_t n, const float* dirs, int64_t dir_div, int64_t dir_stride,
+                            const float* x_c, const float* jac, const float* g_c, const float* rgb,
+                            const uint8_t* stash, const float* sdf_bar, const float* gc_bar, const float* jac_bar,
+                            const float* rgb_bar, const es_train_params* prm, void* stream);
+
+struct es_render_out;
+/* Adjoints of the render outputs (any may be NULL); gradient_o_error: device scalar. */
+typedef struct es_render_grads {
+  const float* color_map;        /* [R,3] */
+  const float* depth_map;        /* [R] */
+  const float* gradients_o;      /* [R,M,3] */
+  const float* gradient_o_error; /* [1] */
+  const float* weights;          /* [R,M] */
+  const float* cdf;              /* [R,M] */
+  const float* sdf;              /* [R,M] */
+  const float* sampled_color;    /* [R,M,3] */
+} es_render_grads;
+
+/* render_core (endosurf.py:134-213) on given sample positions z_vals [R,M] with everything the backward needs kept:
+ * x_c [P,3], jac [P,9] (NULL without deform), sdf [P], g_c [P,3], rgb [P,3] (P = R M) are outputs the caller keeps,
+ * eik_den [1] receives sum(relax) + 1e-6.  `out` as in es_render_rays (8 required keys). */
+int es_render_train_forward(es_ctx* ctx, const float* rays, int64_t n_rays, const float* z_vals, int32_t m,
+                            int32_t n_samples, float cos_anneal_ratio, const float* variance, float* x_c, float* jac,
+                            float* sdf, float* g_c, float* rgb, uint8_t* stash, const struct es_render_out* out,
+                            float* eik_den, void* stream);
+/* Its reverse.  variance_grad [1] receives d loss / d variance through inv_s (the caller adds s_val's own path). */
+int es_render_train_backward(es_ctx* ctx, const float* rays, int64_t n_rays, const float* z_vals, int32_t m,
+                             int32_t n_samples, float cos_anneal_ratio, const float* variance, const float* x_c,
+                             const float* jac, const float* sdf, const float* g_c, const float* rgb,
+                             const uint8_t* stash, const float* eik_den, const es_render_grads* bar,
+                             const es_train_params* prm, float* variance_grad, void* stream);
 
 /* EndoSurfRenderer.up_sample (endosurf.py:221-266) incl. sample_pdf(det=True) (utils.py:160-191).
  * rays [R,9]; z, sdf [R,n]; u_vals [n_imp] = linspace(.5/n_imp, 1-.5/n_imp); new_z [R,n_imp]. */
@@ -137,11 +185,13 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
 /* Per-kernel device timing for bench.py's roofline: when enabled every fused MLP-chain launch is bracketed with
  * CUDA events on the launching stream.  es_profile_read synchronises the stream, returns the accumulated durations
  * since the last read and resets them.  kind: 0 = geometry chain (deform+sdf with tangent rows and feature layer),
- * 1 = colour chain, 2 = sdf query chain, 3/4/5 = reverse (training) chain of the deform / sdf / colour network. */
+ * 1 = colour chain, 2 = sdf query chain, 3/4/5 = reverse (training) chain of the deform / sdf / colour network,
+ * 6 = input-adjoint launches, 7 = weight-gradient kernel, 8 = its reduce + weight-norm backward, 9 = compositing
+ * forward / backward, 10 = 3-wide output-layer gradients. */
 typedef struct es_profile {
-  double ms[6];
-  int64_t launches[6];
-  int64_t points[6];
+  double ms[12];
+  int64_t launches[12];
+  int64_t points[12];
 } es_profile;
 int es_profile_enable(es_ctx* ctx, int32_t on);
 int es_profile_read(es_ctx* ctx, es_profile* out, void* stream);
@@ -152,6 +202,17 @@ int64_t es_launch_count(const es_ctx* ctx);
 /* Weight-column order of the kernel's encoder chunks: fills out[64] with the reference input column each of the
  * 64 chunk columns reads for network `net` (or -1 for padding).  src: 1 deform enc, 2 sdf enc, 3 colour A, 4 colour B. */
 int es_chunk_colmap(const es_ctx* ctx, int net, int src, int32_t* out64);
+
+/* Self-test of the weight-gradient kernel on caller-built plane records (tests/test_gpu_wgrad.py):
+ * out[256][64 n_b] = zbar^T in over n_tiles 128-row tiles, zbar_rec = [tile][4 chunks][16 KiB],
+ * in_rec = [tile][n_b chunks][16 KiB]; bias_out[256] = column sums of zbar over all rows (bias_mode 1) or over the
+ * primal rows 32Q + p of every tile (bias_mode 2).  Synchronises the stream. */
+int es_wgrad_probe(es_ctx* ctx, const uint8_t* zbar_rec, const uint8_t* in_rec, int64_t n_tiles, int32_t n_b,
+                   int32_t bias_mode, float* out, float* bias_out, void* stream);
+
+/* Debug knobs: key 0 = ablation flags (ES_ABLATE builds), 1 / 2 = LBO / SBO bytes of the weight-gradient kernel's
+ * MN-major operand descriptors (0 = built-in 128 / 2048; the parity test checks the convention on hardware). */
+int es_debug_set(es_ctx* ctx, int32_t key, int32_t value);
 
 /* Debug: pipeline trace of CTA 0 of the next fused-chain launches.  host_out == NULL arms it; a second call with a
  * buffer of 1 + 2*capacity_pairs int64 copies out [count, (clock64, code) ...] and disarms (tools/trace_chain.py). */

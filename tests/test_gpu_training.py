@@ -10,15 +10,16 @@ from conftest import load_npz, assert_close, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _renderer(cfg, ckpt, ns, ni, use_deform=True):
-    from endosurf_b200 import EndoSurfRenderer
+def _renderer(cfg, ckpt, ns, ni, use_deform=True, full_planes=False, precision_terms=3):
+    from endosurf_b200 import EndoSurfRenderer, _lib
     rc = copy.deepcopy(cfg["render"])
     rc.update(n_samples=ns, n_importance=ni, perturb=False)
     nc = copy.deepcopy(cfg["net"])
     nc["use_deform"] = use_deform
-    r = EndoSurfRenderer(rc, nc, device="cuda")
+    r = EndoSurfRenderer(rc, nc, device="cuda", precision_terms=precision_terms)
     r.load_checkpoint({k: v for k, v in ckpt.items() if use_deform or k != "deform_network"})
     r.train()
+    _lib.check(r._context(), _lib.load().es_set_plane_mode(r._context(), int(full_planes)), "es_set_plane_mode")
     return r, rc, nc
 
 
@@ -43,9 +44,12 @@ def _my_grads(r, loss):
 
 def _compare(mine, ref, tol_norm=1e-2, tol_global=1e-3):
     """every parameter tensor: ||g - g_ref|| / ||g_ref|| <= tol_norm (Adam normalises per tensor), and the whole
-    gradient vector within tol_global.  The loose per-tensor bound covers the early colour/deform layers whose
-    gradients are 1e4 x smaller than the rest and see the ReLU-gate flips discussed in conftest.assert_close."""
+    gradient vector within tol_global.  On tiny batches the per-tensor bound has to cover single ReLU-gate flips of
+    the deformation net (conftest.assert_close); the batch-size tests below hold the timed path to 1e-3 / 1e-4."""
     worst = []
+    for k in ref:
+        if mine.get(k) is not None:
+            assert torch.isfinite(mine[k]).all(), f"non-finite gradient for {k}"
     num = sum(((mine[k] - g) ** 2).sum().item() for k, g in ref.items() if g is not None and mine[k] is not None)
     den = sum((g ** 2).sum().item() for g in ref.values() if g is not None)
     assert (num / max(den, 1e-30)) ** 0.5 <= tol_global, f"global gradient error {(num / den) ** 0.5:.3e}"
@@ -63,15 +67,15 @@ def _compare(mine, ref, tol_norm=1e-2, tol_global=1e-3):
     return worst[:5]
 
 
-@pytest.mark.parametrize("use_deform", [True, False])
-def test_point_field_gradients(cfg, ckpt, use_deform):
+@pytest.mark.parametrize("use_deform,full_planes", [(True, False), (False, False), (True, True)])
+def test_point_field_gradients(cfg, ckpt, use_deform, full_planes):
     """Random adjoints on every output of the point pipeline (sdf, g_o, rgb) at explicit points."""
     s = load_npz("stage_points.npz")
     n = 96
     x, d, t = (torch.from_numpy(s[k][:n]) for k in "xdt")
     g = torch.Generator().manual_seed(3)
     a_sdf, a_go, a_rgb = torch.randn(n, 1, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
-    r, rc, nc = _renderer(cfg, ckpt, 32, 32, use_deform)
+    r, rc, nc = _renderer(cfg, ckpt, 32, 32, use_deform, full_planes)
 
     def oracle_loss(orc, net):
         raw = net.forward(torch.cat([x, d, t], -1))
@@ -88,12 +92,14 @@ def test_point_field_gradients(cfg, ckpt, use_deform):
     _compare(mine, ref)
 
 
-@pytest.mark.parametrize("tag,use_deform", [("r32_s32_i32_it25k", True), ("r32_nodeform_s32_i32", False)])
-def test_render_rays_training_gradients(cfg, ckpt, tag, use_deform):
+@pytest.mark.parametrize("tag,use_deform,full_planes", [("r32_s32_i32_it25k", True, False),
+                                                        ("r32_nodeform_s32_i32", False, False),
+                                                        ("r32_s32_i32_it25k", True, True)])
+def test_render_rays_training_gradients(cfg, ckpt, tag, use_deform, full_planes):
     """d loss / d every parameter for loss = 0.7 sum(color) + 0.3 sum(depth) + 0.1 eikonal on fixed z_vals."""
     g = load_npz(f"render_{tag}.npz")
     ns, ni = int(g["n_samples"]), int(g["n_importance"])
-    r, rc, nc = _renderer(cfg, ckpt, ns, ni, use_deform)
+    r, rc, nc = _renderer(cfg, ckpt, ns, ni, use_deform, full_planes)
     rays = torch.from_numpy(g["rays"])
     z = torch.from_numpy(g["z_vals"])
     it = int(g["iter_step"])
@@ -137,72 +143,106 @@ def test_training_step_changes_loss(cfg, ckpt):
     assert losses[-1] < losses[0]
 
 
-def test_plane_gemm_fast_paths():
-    """The tensor-core library GEMMs the training glue uses above FAST_MIN_ROWS (the unit batches above are below it)
-    against float64 products of the same hi/lo planes."""
-    from endosurf_b200 import training as T
-    g = torch.Generator().manual_seed(5)
-    rows = 2 * T.FAST_MIN_ROWS
-    a = (torch.randn(rows, 256, generator=g) * torch.rand(rows, 1, generator=g)).cuda()
-    b = torch.randn(rows, 256, generator=g).cuda()
-    (ah, al), (bh, bl) = T.split16(a), T.split16(b)
-    a64 = ah.double() + al.double()
-    b64 = bh.double() + bl.double()
-    ref = a64.t() @ b64
-    old = T.WGRAD_TERMS
-    try:
-        # 3 terms: products exact to 2^-22, the rest is the fp32 (split-K) accumulation over 65536 rows
-        for terms, tol in ((3, 2e-5), (1, 1e-3)):
-            T.WGRAD_TERMS = terms
-            out = T.tn_planes(ah, al, bh, bl)
-            assert T._MM_OUT_DTYPE_OK, "fp16 GEMM with fp32 output is not available: the fast path did not run"
-            e = ((out.double() - ref).norm() / ref.norm()).item()
-            assert e < tol, f"tn_planes terms={terms}: rel err {e:.3e}"
-    finally:
-        T.WGRAD_TERMS = old
-    w = torch.randn(256, 39, generator=g).cuda()
-    out = T.planes_mm(ah, al, w)
-    ref = a64 @ w.double()
-    e = ((out.double() - ref).norm() / ref.norm()).item()
-    assert e < 2e-5, f"planes_mm: rel err {e:.3e}"
-    sel = (torch.rand(1, rows, generator=g) < 0.25).to(torch.float16).cuda()
-    ref = (sel.double() @ a64)[0]
-    try:
-        for terms, tol in ((3, 2e-5), (1, 1e-3)):
-            T.WGRAD_TERMS = terms
-            out = T.rowsum_planes(ah, al, sel)
-            e = ((out.double() - ref).norm() / ref.norm()).item()
-            assert e < tol, f"rowsum_planes terms={terms}: rel err {e:.3e}"
-    finally:
-        T.WGRAD_TERMS = old
+def _trainer_loss(o, color_gt, depth_gt, mask):
+    """The colour / depth / eikonal terms of the reference trainer with its mean normalisation
+    (trainer_endosurf.py:131-152; weights of configs/endosurf/baseline/base_pull.yml), which makes the adjoints that
+    enter the backward 1e-5 .. 1e-8."""
+    import torch.nn.functional as F
+    ce = (o["color_map"] - color_gt) * mask
+    color_loss = F.l1_loss(ce, torch.zeros_like(ce), reduction="sum") / (mask.sum() + 1e-10)
+    de = (o["depth_map"] - depth_gt) * mask
+    depth_loss = F.l1_loss(de, torch.zeros_like(de), reduction="sum") / (mask.sum() + 1e-10)
+    return color_loss * 1.0 + depth_loss * 1.0 + o["gradient_o_error"] * 0.1
 
 
-def test_graphed_train_step(cfg, ckpt):
-    """A CUDA-graph replay of forward + loss + backward gives the gradients of the eager step on NEW inputs."""
+@pytest.mark.parametrize("it", [0, 50000])
+def test_timed_path_gradient_parity_512_rays(cfg, ckpt, it):
+    """Gradient parity of exactly what bench.py times: default plane mode (fp16 hi planes, 1-term tcgen05 weight
+    gradients), 512 rays x (64+64) samples = 65,536 points (262,144 geometry rows), the trainer's mean-normalised
+    losses, fixed z_vals, all 82 parameter tensors against the oracle's autograd.
+    Tolerances: every tensor <= 1e-3 relative norm, whole gradient vector <= 1e-4... see DESIGN.md section 6 for why the
+    hi-only products reach this (zero-mean rounding averaged over >= 6.5e4 rows)."""
     from oracle import endosurf_oracle as orc
-    from endosurf_b200.training import GraphedTrainStep
-    r, rc, nc = _renderer(cfg, ckpt, 16, 16)
-    target0 = torch.full((64, 3), 0.25, device="cuda")
-    target1 = torch.full((64, 3), 0.6, device="cuda")
-    rays0 = orc.synthetic_rays(64, frame=2, seed=4).cuda()
-    rays1 = orc.synthetic_rays(64, frame=5, seed=9).cuda()
+    r, rc, nc = _renderer(cfg, ckpt, 64, 64)
+    R = 512
+    rays = orc.synthetic_rays(R, frame=7, seed=11)
+    g = torch.Generator().manual_seed(12)
+    color_gt = torch.rand(R, 3, generator=g)
+    depth_gt = torch.rand(R, 1, generator=g) * 0.5 + 0.5
+    mask = (torch.rand(R, 1, generator=g) < 0.8).float()
+    with torch.no_grad():
+        z = r._sample_z(rays.cuda(), it, False).cpu()
 
-    def lossf(o, tgt):
-        return (o["color_map"] - tgt).abs().mean() + 0.1 * o["gradient_o_error"] + 0.05 * o["depth_map"].mean()
+    def oracle_loss(orc_, net):
+        return _trainer_loss(orc_.render_rays(net, rc, rays, iter_step=it, perturb_overwrite=False, z_vals_override=z),
+                             color_gt, depth_gt, mask)
 
-    gstep = GraphedTrainStep(r, lossf, rays0, (target0,), iter_step=1000)
-    out, loss = gstep(rays1, target1)
-    torch.cuda.synchronize()
-    g_graph = {n: p.grad.detach().clone() for n, p in r.model.named_parameters() if p.grad is not None}
-    loss_graph, color_graph = loss.item(), out["color_map"].clone()
-    r.zero_grad()
-    o = r(rays1, iter_step=1000)
-    l = lossf(o, target1)
-    l.backward()
+    ref_loss, ref = _oracle_grads(ckpt, nc, oracle_loss)
+    o = r.render_rays(rays.cuda(), iter_step=it, perturb_overwrite=False, z_vals_override=z.cuda())
+    loss = _trainer_loss(o, color_gt.cuda(), depth_gt.cuda(), mask.cuda())
+    assert rel_err(loss.detach(), ref_loss) < 1e-4
+    mine = _my_grads(r, loss)
     r.sync_check()
-    assert rel_err(color_graph, o["color_map"].detach()) < 1e-6
-    assert abs(loss_graph - l.item()) <= 1e-6 * abs(l.item())
-    assert set(g_graph) == {n for n, p in r.model.named_parameters() if p.grad is not None}
-    num = sum(((g_graph[n] - p.grad) ** 2).sum().item() for n, p in r.model.named_parameters() if p.grad is not None)
-    den = sum((p.grad ** 2).sum().item() for p in r.model.parameters() if p.grad is not None)
-    assert (num / den) ** 0.5 < 1e-5, f"graph replay gradients differ from eager: {(num / den) ** 0.5:.3e}"
+    worst = _compare(mine, ref, tol_norm=1e-3, tol_global=1e-4)
+    print("worst tensors:", worst)
+
+
+def test_perturbed_sampling_with_injected_jitter(cfg, ckpt):
+    """perturb=True: the per-ray jitter is drawn with torch.rand on the device like the reference (endosurf.py:81); with
+    the same numbers injected into the oracle the sample positions and the rendered outputs agree."""
+    from oracle import endosurf_oracle as orc
+    r, rc, nc = _renderer(cfg, ckpt, 32, 32)
+    R = 64
+    rays = orc.synthetic_rays(R, frame=3, seed=5)
+    torch.manual_seed(123)
+    t_rand = (torch.rand([R, 1], device="cuda") - 0.5).cpu()
+    torch.manual_seed(123)
+    with torch.no_grad():
+        z = r._sample_z(rays.cuda(), 50000, True).cpu()
+    net = orc.OracleNet(ckpt, nc)
+    with torch.no_grad():
+        ref = orc.render_rays(net, rc, rays, iter_step=50000, perturb_overwrite=True, t_rand=t_rand)
+    # hierarchical resampling is discontinuous in the coarse sdf: quantile gate as in test_gpu_parity
+    assert_close("z_vals(perturb)", z, ref["z_vals"], 1e-4, kink_tol=5e-2, q=0.98)
+    # coarse samples carry exactly the jitter: first / last sample positions per ray move by t_rand * 2/n_samples
+    with torch.no_grad():
+        z0 = r._sample_z(rays.cuda(), 50000, False).cpu()
+    assert not torch.equal(z, z0)
+
+
+def test_single_pass_fp16_forward_and_gradients(cfg, ckpt):
+    """precision_terms=1 (one fp16 tensor-core pass instead of the 3-term split, the bf16/fp16 training config):
+    forward within 5e-3 of the oracle, gradients within 5e-2 per tensor / 2e-2 overall."""
+    g = load_npz("render_r32_s32_i32_it25k.npz")
+    ns, ni = int(g["n_samples"]), int(g["n_importance"])
+    r, rc, nc = _renderer(cfg, ckpt, ns, ni, True, False, precision_terms=1)
+    rays = torch.from_numpy(g["rays"])
+    z = torch.from_numpy(g["z_vals"])
+    it = int(g["iter_step"])
+
+    def lossf(o):
+        return o["color_map"].sum() * 0.7 + o["depth_map"].sum() * 0.3 + o["gradient_o_error"] * 0.1
+
+    ref_loss, ref = _oracle_grads(ckpt, nc, lambda orc, net: lossf(
+        orc.render_rays(net, rc, rays, iter_step=it, perturb_overwrite=False, z_vals_override=z)))
+    o = r.render_rays(rays.cuda(), iter_step=it, perturb_overwrite=False, z_vals_override=z.cuda())
+    for k in ["color_map", "depth_map"]:
+        assert_close(k, o[k].detach(), g["core/" + k], 5e-3, kink_tol=5e-2)
+    mine = _my_grads(r, lossf(o))
+    r.sync_check()
+    _compare(mine, ref, tol_norm=5e-2, tol_global=2e-2)
+
+
+def test_training_launch_budget(cfg, ckpt):
+    """One training step of render_rays (forward + backward) stays within 60 library launches after the sampling, and
+    none of them is a PyTorch / library GEMM kernel (the library counts its own launches)."""
+    from oracle import endosurf_oracle as orc
+    r, rc, nc = _renderer(cfg, ckpt, 16, 16)
+    rays = orc.synthetic_rays(64, frame=2, seed=4).cuda()
+    with torch.no_grad():
+        z = r._sample_z(rays, 1000, False)
+    n0 = r.launch_count()
+    o = r.render_rays(rays, iter_step=1000, z_vals_override=z)
+    (o["color_map"].sum() + o["gradient_o_error"]).backward()
+    r.sync_check()
+    assert r.launch_count() - n0 <= 60, r.launch_count() - n0
