@@ -96,6 +96,9 @@ struct es_ctx {
   // lo halves the input-adjoint launches need; 1 = every lo plane (3-term weight gradients, exact gates)
   int full_planes = 0;
   int wgrad_lbo = 0, wgrad_sbo = 0;   // debug override of the MN-major descriptor strides (0: built-in)
+  float scale_target = 1024.f;        // the largest adjoint entering a reverse chain is scaled to about this:
+                                      // 64x below the fp16 maximum (conversions saturate), and small adjoints
+                                      // stay above the fp16 subnormal floor (tools/diag_grad_precision.py)
   // optional per-kernel timing (es_profile_*)
   bool profiling = false;
   int debug_flags = 0;
@@ -1068,7 +1071,9 @@ int get_wgrad_plan(es_ctx* ctx, int64_t n, es_ctx::WgradPlan** out) {
   const int n_terms = full ? 3 : 1;
   long long total_work = 0;
   for (auto& pr : protos) total_work += pr.tiles * n_terms;
-  const long long slice_tiles = std::max<long long>(16, (total_work + ctx->n_sms * 4 - 1) / (ctx->n_sms * 4));
+  // short split-K slices: the tensor core accumulates in fp32 with truncation, whose bias grows with the length of one
+  // accumulation chain; the partial tiles are summed by the reduce kernel in round-to-nearest fp32
+  const long long slice_tiles = std::max<long long>(16, (total_work + ctx->n_sms * 16 - 1) / (ctx->n_sms * 16));
   es_ctx::WgradPlan wp;
   wp.n = n;
   wp.full = ctx->full_planes;
@@ -1233,7 +1238,7 @@ int backward_core(es_ctx* ctx, const BwdIn& a, const BwdScratch& s, es_ctx::Wgra
   };
   auto set_scale = [&](int net, const float* adj, long long count) -> int {
     CU(launch_amax(adj, count, ctx->amax_dev + net, stream));
-    CU(launch_scale_from_amax(ctx->amax_dev + net, ctx->scale_dev + net, stream));
+    CU(launch_scale_from_amax(ctx->amax_dev + net, ctx->scale_dev + net, ctx->scale_target, stream));
     ctx->launches += 2;
     return 0;
   };
@@ -1557,6 +1562,7 @@ int es_debug_set(es_ctx* ctx, int32_t key, int32_t value) {
     case 0: ctx->debug_flags = value; return 0;   // ES_ABLATE builds only
     case 1: ctx->wgrad_lbo = value; return 0;     // MN-major descriptor strides of the weight-gradient kernel
     case 2: ctx->wgrad_sbo = value; return 0;
+    case 3: ctx->scale_target = std::ldexp(1.f, value); return 0;  // adjoint scale target 2^value
     default: return ES_E_BADARG;
   }
 }

@@ -268,12 +268,17 @@ __device__ __forceinline__ bool elect_one_sync() {
 // Products of two fp16 values are exact in the fp32 accumulator.  Range: |x| must stay below 65504 (activations,
 // tangents and weights of these weight-normalised 256-wide MLPs are O(1..100)); tiny values lose nothing that
 // matters because the error is absolute (fp16 subnormal spacing 6e-8).
+// The conversion saturates (F2FP.SATFINITE): an adjoint that outgrows the fp16 range inside a reverse chain is
+// clipped to +-65504 instead of turning every later gradient into NaN.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {  // a -> low half, b -> high half
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(a, b);
-  float2 hf = __half22float2(h);
-  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
+  hi = pack_f16x2_sat(a, b);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16x2_sat(a - hf.x, b - hf.y);
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -144,7 +144,7 @@ cudaError_t launch_smallm_reduce(const float* part, int n_blocks, int j0, int nj
 cudaError_t launch_wn_backward(const WnLayers& layers, int max_rows, cudaStream_t stream);
 cudaError_t launch_wn_fold(const WnLayers& layers, int max_rows, cudaStream_t stream);
 cudaError_t launch_amax(const float* p, long long n, unsigned int* amax_bits, cudaStream_t stream);
-cudaError_t launch_scale_from_amax(const unsigned int* amax_bits, float* scale, cudaStream_t stream);
+cudaError_t launch_scale_from_amax(const unsigned int* amax_bits, float* scale, float target, cudaStream_t stream);
 
 // ---- per-ray kernels (es_rays.cu)
 struct RayGeom {

@@ -309,7 +309,11 @@ static __device__ __noinline__ void encode_chunk(uint32_t slot_sa, int src, int 
       }
     }
   });
-  if (src == SRC_COLOR_B && PCOLS * part >= 32) return;
+  if (src == SRC_COLOR_B && PCOLS * part >= 32) {
+    // no weights for these columns; keep the slot (and the training record made from it) free of stale values
+#pragma unroll
+    for (int i = 0; i < PCOLS; ++i) v[i] = 0.f;
+  }
   emit_row(slot_sa + 2 * part * A_LBO + row * 16, v);
 }
 

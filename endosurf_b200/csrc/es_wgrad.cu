@@ -349,12 +349,13 @@ __global__ void amax_kernel(const float* __restrict__ p, long long n, unsigned i
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
 }
-// scale = 2^floor(log2(16 / amax)): the largest adjoint entering a reverse chain becomes ~16..32, so that the fp16
+// scale = 2^floor(log2(target / amax)): the largest adjoint entering a reverse chain becomes ~target, so that the fp16
 // planes keep their relative precision whatever the loss normalisation (mean losses give adjoints of 1e-5..1e-8)
-__global__ void scale_from_amax_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ scale) {
+__global__ void scale_from_amax_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ scale,
+                                       float target) {
   const float a = __uint_as_float(*amax_bits);
   float s = 1.f;
-  if (a > 0.f && a < 3.0e38f) s = exp2f(floorf(log2f(16.f / a)));
+  if (a > 0.f && a < 3.0e38f) s = exp2f(floorf(log2f(target / a)));
   if (!(s > 0.f) || s > 1.0e30f) s = 1.0e30f;
   *scale = s;
 }
@@ -406,8 +407,8 @@ cudaError_t launch_amax(const float* p, long long n, unsigned int* amax_bits, cu
   amax_kernel<<<static_cast<int>(blocks < 1184 ? blocks : 1184), 256, 0, stream>>>(p, n, amax_bits);
   return cudaGetLastError();
 }
-cudaError_t launch_scale_from_amax(const unsigned int* amax_bits, float* scale, cudaStream_t stream) {
-  scale_from_amax_kernel<<<1, 1, 0, stream>>>(amax_bits, scale);
+cudaError_t launch_scale_from_amax(const unsigned int* amax_bits, float* scale, float target, cudaStream_t stream) {
+  scale_from_amax_kernel<<<1, 1, 0, stream>>>(amax_bits, scale, target);
   return cudaGetLastError();
 }
 

