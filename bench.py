@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""Benchmark of the render_rays hot path (BASELINE.json: rays/sec, 512x512 frames, 64+64 samples).
+"""Benchmark of the render_rays hot path (BASELINE.json: training rays/sec, 512x512 frames, 64+64 samples).
 
-    python bench.py --gpus 1 --steps 20 --warmup 5                 # this repo's CUDA path
-    python bench.py --impl reference --steps 3 --warmup 1          # reference algorithm on the host CPU cores
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        bench.py --gpus N --steps K --warmup W                     # one rank per GPU, weak scaling over ray batches
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # this repo's CUDA path, training step (default)
+    python bench.py --mode forward                                 # inference render_rays
+    python bench.py --mode frame                                   # BASELINE configs[4]: one full 512x512 frame, latency
+    python bench.py --mode grid256                                 # BASELINE configs[4]: 256^3 SDF grid query, latency
+    python bench.py --precision-terms 1                            # BASELINE configs[2]: single-pass fp16 training
+    python bench.py --impl reference --steps 3 --warmup 1          # the UNMODIFIED reference on the host CPU cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
+        bench.py --gpus N --steps K --warmup W                     # one rank per GPU, ray shards (weak scaling)
 
-A step is one render_rays call on a batch of `--rays` synthetic rays of one 512x512 frame (configs[1] of
-BASELINE.json: 4096 rays, 64 coarse + 64 fine samples, 4 up-sampling steps, 9x256 networks, fp32 parity mode).
-Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for what every key means.
+A training step is: render_rays forward on a batch of `--rays` synthetic rays of one 512x512 frame (configs[1] of
+BASELINE.json: 4096 rays, 64 coarse + 64 fine samples, 4 up-sampling steps, 9x256 networks, fp32-parity mode), the
+reference trainer's masked-mean colour / depth losses + eikonal term, backward, (N > 1: the data-parallel gradient
+all-reduce of endosurf_b200.distributed) and Adam.  Rank 0 prints ONE JSON line.  DESIGN.md section 7 explains every key.
 """
 from __future__ import annotations
 
@@ -37,6 +42,13 @@ def flops_per_ray(ns, ni, steps):
     return 2.0 * (u * (D_MAC + S_MAC) + m * (4 * D_MAC + 2 * S_MAC + C_MAC))
 
 
+def train_flops_per_ray(ns, ni, steps):
+    """SURVEY 8d convention: up-sampling x1 + render_core x3 (forward + ~2x backward)."""
+    m = ns + ni
+    u = ns + (steps - 1) * ni // steps if ni > 0 else 0
+    return 2.0 * (u * (D_MAC + S_MAC) + 3 * m * (4 * D_MAC + 2 * S_MAC + C_MAC))
+
+
 NET_CFG = {
     "bound": 1.0, "use_deform": True,
     "deform_network": {"enc_pos_cfg": {"enc_type": "frequency", "input_dim": 3, "multires": 6},
@@ -53,12 +65,22 @@ NET_CFG = {
 RENDER_CFG = {"type": "endosurf", "net_chunk": 80000, "anneal_end": 50000, "n_samples": 64, "n_importance": 64,
               "important_begin_iter": 0, "up_sample_steps": 4, "perturb": True}
 ITER_STEP = 50000
+HW = 512
+
+METRICS = {"train": "training rays/sec (512x512 frames, 64+64 samples)",
+           "forward": "render_rays forward rays/sec (512x512 frames, 64+64 samples)",
+           "frame": "inference latency of one full 512x512 frame (64+64 samples)",
+           "grid256": "latency of the 256^3 marching-cubes SDF grid query"}
 
 
-def make_rays(n_rays, frame, hw=512, n_frames=60, seed=0):
+def make_rays(n_rays, frame, hw=HW, n_frames=60, seed=0, all_pixels=False):
     """Pinhole rays from o=(0,0,-1.5) over a 512x512 image (focal 1.2*W), one frame per batch, time=frame/59."""
-    g = torch.Generator().manual_seed(seed + 7919 * frame)
-    pix = torch.randint(0, hw * hw, (n_rays,), generator=g)
+    if all_pixels:
+        pix = torch.arange(hw * hw)
+        n_rays = hw * hw
+    else:
+        g = torch.Generator().manual_seed(seed + 7919 * frame)
+        pix = torch.randint(0, hw * hw, (n_rays,), generator=g)
     u = (pix % hw).float() + 0.5
     v = (pix // hw).float() + 0.5
     f = 1.2 * hw
@@ -69,21 +91,27 @@ def make_rays(n_rays, frame, hw=512, n_frames=60, seed=0):
 
 
 def make_targets(n_rays, frame, seed=0):
+    """colour [R,3], depth [R,1], mask [R,1] (about 85 % of the pixels carry a valid colour/depth, like an endoscopic
+    frame with tool masks)."""
     g = torch.Generator().manual_seed(seed + 31 * frame + 5)
-    return torch.rand(n_rays, 3, generator=g), 0.5 + 0.5 * torch.rand(n_rays, 1, generator=g)
+    return (torch.rand(n_rays, 3, generator=g), 0.5 + 0.5 * torch.rand(n_rays, 1, generator=g),
+            (torch.rand(n_rays, 1, generator=g) < 0.85).float())
 
 
-def train_loss(o, color_gt, depth_gt):
-    """L1 colour + L1 depth + 0.1 eikonal: the render_rays part of the reference loss (trainer_endosurf.py:132-162)."""
-    return (o["color_map"] - color_gt).abs().mean() + (o["depth_map"] - depth_gt).abs().mean() + \
-        0.1 * o["gradient_o_error"]
+def train_loss(o, color_gt, depth_gt, mask):
+    """The render_rays part of the reference loss with its masked-mean normalisation (trainer_endosurf.py:131-152,
+    weights of configs/endosurf/baseline/base_pull.yml): L1 colour + L1 depth + 0.1 eikonal."""
+    ce = (o["color_map"] - color_gt) * mask
+    de = (o["depth_map"] - depth_gt) * mask
+    den = mask.sum() + 1e-10
+    return ce.abs().sum() / den + de.abs().sum() / den + 0.1 * o["gradient_o_error"]
 
 
-def seeded_state(renderer_module):
+def seeded_state(module):
     """Random-init weights of the reference architecture: geometric SDF init + seeded noise (a deforming surface)."""
     g = torch.Generator().manual_seed(1234)
     with torch.no_grad():
-        for n, p in renderer_module.named_parameters():
+        for n, p in module.named_parameters():
             s = 0.004 if "sdf_network" in n else 0.02
             p.add_(s * torch.randn(p.shape, generator=g).to(p.device))
 
@@ -124,47 +152,91 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def measured_peak_tflops():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             j = json.load(f)
-        return float(j.get("bf16_tflops_sustained", j.get("bf16_tflops"))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
-    return 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
+        return (float(j.get("bf16_tflops_sustained", j.get("bf16_tflops"))),
+                "measured (MEASURED_PEAKS.json bf16_tflops_sustained)", float(j.get("hbm_gbs", 6500.0)))
+    return 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)", 6500.0
 
 
-def oracle_cpu_rays_per_s(n_rays, repeats, threads, mode="train"):
-    """Reference algorithm (oracle port; the reference is pure Python/PyTorch and cannot travel) on the host CPU."""
-    from oracle import endosurf_oracle as orc  # checker / baseline only
-    from endosurf_b200 import EndoSurfNet
-    torch.set_num_threads(threads)
+def ncu_traffic(mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel at this workload's size, read
+    from the committed ncu capture summary (profiles/r2_ncu_traffic.json, written by tools/ncu_traffic.py from the
+    `ncu --set full` report); null when no capture of the current kernels has been committed."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(mode, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------ the reference itself
+def _reference_renderer(device, train=True):
+    """The UNMODIFIED reference renderer (byte-compiled under oracle/_ref, SURVEY 8c shims) with the same seeded
+    random-init state as our arm; falls back to the oracle port when oracle/_ref has not been built."""
+    from oracle import ref_shims  # baseline infrastructure only
     torch.manual_seed(0)
+    if ref_shims.available():
+        mod = ref_shims.load_reference()
+        r = mod.EndoSurfRenderer(copy.deepcopy(RENDER_CFG), copy.deepcopy(NET_CFG), device)
+        seeded_state(r.model)
+        r.train(train)
+        params = [p for v in r.get_train_params().values() for p in v]
+        return "reference", (lambda rays: r(rays, iter_step=ITER_STEP)), params
+    from oracle import endosurf_oracle as orc
+    from endosurf_b200 import EndoSurfNet
     model = EndoSurfNet(NET_CFG)
     seeded_state(model)
-    train = mode == "train"
-    ck = {k: {kk: vv.detach().clone().requires_grad_(train) for kk, vv in sd.items()}
+    ck = {k: {kk: vv.detach().clone().to(device).requires_grad_(train) for kk, vv in sd.items()}
           for k, sd in model.save_checkpoint().items()}
     net = orc.OracleNet(ck, NET_CFG)
     rc = copy.deepcopy(RENDER_CFG)
-    params = [p for sd in ck.values() for p in sd.values()]
+    return "port", (lambda rays: orc.render_rays(net, rc, rays, iter_step=ITER_STEP)), \
+        [p for sd in ck.values() for p in sd.values()]
+
+
+def reference_rays_per_s(n_rays, steps, warmup, device, mode="train", threads=None):
+    """Time the reference's own PyTorch path (stock ops, fp32, TF32 off) on `device`: rays/s over `steps` steps."""
+    if threads:
+        torch.set_num_threads(threads)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    train = mode == "train"
+    kind, render, params = _reference_renderer(device, train)
     opt = torch.optim.Adam(params, lr=5e-4) if train else None
     times = []
-    for i in range(repeats + 1):
-        rays = make_rays(n_rays, frame=i)
-        cgt, dgt = make_targets(n_rays, frame=i)
+    for i in range(warmup + steps):
+        rays = make_rays(n_rays, frame=i).to(device)
+        cgt, dgt, msk = (x.to(device) for x in make_targets(n_rays, frame=i))
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         if train:
             opt.zero_grad()
-            o = orc.render_rays(net, rc, rays, iter_step=ITER_STEP)
-            loss = train_loss(o, cgt, dgt)
+            o = render(rays)
+            loss = train_loss(o, cgt, dgt, msk)
             loss.backward()
             opt.step()
         else:
             with torch.no_grad():
-                orc.render_rays(net, rc, rays, iter_step=ITER_STEP)
-        times.append(time.perf_counter() - t0)
-    t = float(np.median(times[1:])) if repeats > 0 else times[0]
-    return n_rays / t, t
+                render(rays)
+        if device != "cpu":
+            torch.cuda.synchronize()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    return n_rays / t, t, kind
+
+
+def reference_sample_rays(steps, warmup):
+    """Bounded CPU sample: about 12k rays of CPU work in total (2-3 minutes on a 16-core host), <= 1024 rays per step
+    (the reference keeps every chunk's autograd graph: 4096 rays x 128 samples do not fit a host's memory budget)."""
+    per = 12288 // max(steps + warmup, 1)
+    return int(min(1024, max(128, per // 128 * 128)))
 
 
 def run_reference(args):
@@ -172,79 +244,54 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = args.ref_rays
-    from oracle import endosurf_oracle as orc  # noqa
-    v, _ = oracle_cpu_rays_per_s(n, 0, threads, args.mode)  # warm the allocator / thread pool
-    times = []
-    for _ in range(max(args.warmup - 1, 0)):
-        oracle_cpu_rays_per_s(n, 0, threads, args.mode)
-    for _ in range(args.steps):
-        _, t = oracle_cpu_rays_per_s(n, 0, threads, args.mode)
-        times.append(t)
-    ms = 1e3 * float(np.mean(times))
-    val = n / (ms * 1e-3)
+    n = args.ref_rays or reference_sample_rays(args.steps, args.warmup)
+    mode = args.mode if args.mode in ("train", "forward") else "forward"
+    val, t, kind = reference_rays_per_s(n, args.steps, max(args.warmup, 1), "cpu", mode, threads)
     line = {
-        "impl": "reference", "metric": METRICS[args.mode], "value": val, "unit": "rays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.rays, mode=args.mode),
-        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} rays x (64+64 samples, 4 up-sampling steps) per step, {args.mode}, torch "
-                                   f"{torch.__version__} CPU fp32, {threads} threads"},
+        "impl": "reference", "metric": METRICS[mode], "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.rays, mode, args.precision_terms),
+        "sample": {"rays_per_step": n, "note": "each step is a bounded sample of the workload in `config` (same "
+                   "frame geometry, samples per ray, networks, loss); rays/s is a rate, the batch size only bounds "
+                   "the CPU time and memory of the run"},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": kind,
+                         "sample": f"{n} rays x (64+64 samples, 4 up-sampling steps) per step, {mode}, "
+                                   f"{'the unmodified reference (oracle/_ref, byte-compiled)' if kind == 'reference' else 'oracle port'}"
+                                   f", torch {torch.__version__} CPU fp32, {threads} threads"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel at this workload's size, from the
-# committed ncu --set full captures (profiles/r1_v2_ncu_summary.txt; training: the stash-writing variant, 524288 points,
-# tools/ncu_one_kernel.sh -> profiles/r1_v2_ncu_stash_kernel.txt)
-NCU_TRAFFIC_BYTES = {"forward": 11.487488e6 + 525.844480e6, "train": 0.696432896e9 + 26.990113e9}
-
-METRICS = {"train": "training rays/sec (512x512 frames, 64+64 samples)",
-           "forward": "render_rays forward rays/sec (512x512 frames, 64+64 samples)"}
-METRIC = METRICS["train"]
-
-
-def train_flops_per_ray(ns, ni, steps):
-    """SURVEY 8d convention: up-sampling x1 + render_core x3 (forward + ~2x backward)."""
-    m = ns + ni
-    u = ns + (steps - 1) * ni // steps if ni > 0 else 0
-    return 2.0 * (u * (D_MAC + S_MAC) + 3 * m * (4 * D_MAC + 2 * S_MAC + C_MAC))
-
-
-def workload_config(n_rays, note=None, mode="train"):
-    what = ("training step (render_rays forward + L1 colour/depth + eikonal loss, backward, Adam)" if mode == "train"
-            else "render_rays forward")
+def workload_config(n_rays, mode="train", precision_terms=3, world=1, note=None):
+    what = {"train": "training step (render_rays forward + masked-mean L1 colour/depth + eikonal loss, backward, Adam)",
+            "forward": "render_rays forward",
+            "frame": "inference render of one full 512x512 frame",
+            "grid256": "256^3 SDF grid query (extract_fields)"}[mode]
+    prec = ("fp32-parity (fp16 hi/lo x3) tensor-core mode" if precision_terms == 3 else
+            "single-pass fp16 tensor-core mode (precision_terms=1)")
     c = {"workload": f"{what}, {n_rays}-ray batch of one 512x512 frame, 64 coarse + 64 fine samples, "
-                     "4 up-sampling steps, deform+sdf+colour 9x256 MLPs, fp32-parity (fp16 hi/lo x3) tensor-core mode",
+                     f"4 up-sampling steps, deform+sdf+colour 9x256 MLPs, {prec}",
          "rays_per_step_per_gpu": n_rays, "n_samples": 64, "n_importance": 64, "up_sample_steps": 4,
-         "parallelism": ("rays sharded per rank; one NCCL all-reduce of the flat 1.65 M-float gradient bucket per step"
-                         if mode == "train" else "rays sharded per rank, no data-path collective (forward)"),
-         "l2_policy": "per-step working set (>= 1 GiB of per-point scratch) exceeds the 126 MB L2; ray batches rotate"}
+         "parallelism": ("rays sharded per rank; all-reduce of the loss denominators (3 floats) before the backward and "
+                         "ONE NCCL all-reduce of the flat 1.65 M-float gradient bucket after it "
+                         "(endosurf_b200.distributed)" if mode == "train" else
+                         "rays sharded per rank, no data-path collective"),
+         "l2_policy": "per-step working set (>= 1 GiB of per-point scratch, 20 GB of plane records in training) exceeds "
+                      "the 126 MB L2; ray batches rotate"}
     if mode == "train":
         c["precision"] = ("forward and activation-gradient chains: fp16 hi/lo x3 products (fp32 parity); weight/bias "
                           "gradients: own split-K tcgen05 kernel on the fp16 hi planes, fp32 accumulation; gradient "
                           "parity of this exact configuration against the oracle's autograd at 512 rays x 128 samples: "
-                          "tests/test_gpu_training.py::test_timed_path_gradient_parity_512_rays")
+                          "tests/test_gpu_training.py::test_timed_path_gradient_parity_512_rays") if precision_terms == 3 \
+            else "every tensor-core product single-pass fp16 (tests/test_gpu_training.py::test_single_pass_fp16_*)"
     if note:
         c["note"] = note
     return c
 
 
-def allreduce_gradients(params, world):
-    """Data parallelism over ray batches: ONE all-reduce of the flat gradient bucket per step."""
-    import torch.distributed as dist
-    grads = [p.grad for p in params if p.grad is not None]
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat.div_(world)
-    off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
-
-
+# ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -255,21 +302,27 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from endosurf_b200 import EndoSurfRenderer
+    from endosurf_b200 import distributed as dp
 
-    train = args.mode == "train"
+    mode = args.mode
+    train = mode == "train"
     torch.manual_seed(0)
-    r = EndoSurfRenderer(copy.deepcopy(RENDER_CFG), NET_CFG, device=f"cuda:{local}")
+    r = EndoSurfRenderer(copy.deepcopy(RENDER_CFG), NET_CFG, device=f"cuda:{local}",
+                         precision_terms=args.precision_terms)
     seeded_state(r.model)
     r.train(train)
+    if mode in ("frame", "grid256"):
+        return run_latency(args, r, dev, world, rank)
     params = [p for v in r.get_train_params().values() for p in v]
     opt = torch.optim.Adam(params, lr=5e-4) if train else None
+    bucket = dp.FlatGradBucket(params) if train else None
     R, K, W = args.rays, args.steps, args.warmup
     n_batches = min(K + W, 16)
     frames = [(rank * 17 + i) % 60 for i in range(n_batches)]
     host = [make_rays(R, frame=f, seed=rank).pin_memory() for f in frames]
     host_t = [tuple(x.pin_memory() for x in make_targets(R, frame=f, seed=rank)) for f in frames]
     devb = [h.to(dev) for h in host]
-    devt = [(c.to(dev), d.to(dev)) for c, d in host_t]
+    devt = [tuple(x.to(dev) for x in t) for t in host_t]
     out_c = torch.empty(R, 3).pin_memory()
     out_d = torch.empty(R, 1).pin_memory()
     out_l = torch.empty(()).pin_memory()
@@ -279,39 +332,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    graph_err = ""
-
-    def step(rays, cgt, dgt):
+    def step(rays, cgt, dgt, msk):
         if train:
-            opt.zero_grad(set_to_none=True)
             o = r(rays, iter_step=ITER_STEP)
-            loss = train_loss(o, cgt, dgt)
-            loss.backward()
-            if world > 1:
-                allreduce_gradients(params, world)
+            terms, eps = dp.render_loss_terms(r, o, cgt, dgt, msk, msk)
+            logs = dp.dp_backward(bucket, terms, eps)  # world == 1: no collective, same code path
             opt.step()
-            return o, loss
+            return o, logs["loss"]
         with torch.no_grad():
             return r.render_rays(rays, iter_step=ITER_STEP), None
 
     for i in range(W):
         step(devb[i % n_batches], *devt[i % n_batches])
     r.sync_check()
-    # ---------------- per-kernel roofline: CUDA events around every fused-chain launch, eager steps of the same workload
+    # ---------------- device-resident timing (value); CUDA events around every library kernel of the timed region
     r.profile(True)
     r.profile_read()
     launches0 = r.launch_count()
-    n_prof = min(K, 4)
-    for i in range(n_prof):
-        step(devb[(W + i) % n_batches], *devt[(W + i) % n_batches])
-    prof = r.profile_read()
-    launches_per_step = (r.launch_count() - launches0) / n_prof
-    r.profile(False)
-    graphed = None
-    if graphed is None:  # eager steps: the kernel events are taken over the timed region itself
-        r.profile(True)
-        r.profile_read()
-    # ---------------- device-resident timing (value)
     clocks = ClockSampler(local)
     sync_all()
     if rank == 0:
@@ -324,18 +361,17 @@ def run_ours(args):
     sync_all()
     ms_total = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
-    launches = launches_per_step * K
-    if graphed is None:
-        prof, n_prof = r.profile_read(), K
-        r.profile(False)
+    launches = r.launch_count() - launches0
+    prof = r.profile_read()
+    r.profile(False)
     # ---------------- end to end: pinned host rays (+ targets) in, colour + depth (+ loss) back to the host, every step
     sync_all()
     t0 = time.perf_counter()
     for i in range(K):
         j = (W + i) % n_batches
         rays = host[j].to(dev, non_blocking=True)
-        cgt, dgt = (x.to(dev, non_blocking=True) for x in host_t[j])
-        o, loss = step(rays, cgt, dgt)
+        tg = tuple(x.to(dev, non_blocking=True) for x in host_t[j])
+        o, loss = step(rays, *tg)
         out_c.copy_(o["color_map"].detach(), non_blocking=True)
         out_d.copy_(o["depth_map"].detach(), non_blocking=True)
         if loss is not None:
@@ -353,53 +389,156 @@ def run_ours(args):
     if rank == 0:
         value = world * R / (ms_step * 1e-3)
         e2e = world * R / (e2e_ms_step * 1e-3)
-        peak, peak_src = measured_peak_tflops()
+        peak, peak_src, _ = measured_peaks()
         g = prof["geometry_chain"]
         pts_per_launch = g["points"] / max(g["launches"], 1)
         alg_flops_launch = pts_per_launch * 2.0 * (4 * D_MAC + 2 * S_MAC)
         ms_launch = g["ms"] / max(g["launches"], 1)
         achieved = alg_flops_launch / (ms_launch * 1e-3) / 1e12 if ms_launch > 0 else 0.0
-        kern_ms = {k: round(v["ms"] / n_prof, 4) for k, v in prof.items()}
+        kern_ms = {k: round(v["ms"] / K, 4) for k, v in prof.items()}
         fpr = train_flops_per_ray(64, 64, 4) if train else flops_per_ray(64, 64, 4)
-        h2d = R * 9 * 4 + (R * 4 * 4 if train else 0)
+        h2d = R * 9 * 4 + (R * 5 * 4 if train else 0)
         d2h = R * 4 * 4 + (4 if train else 0)
+        terms_note = ("3 fp16 MMAs per product (hi/lo split)" if args.precision_terms == 3 else "1 fp16 MMA per product")
         line = {
-            "metric": METRICS[args.mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRICS[mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (fp16 hi/lo x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
-            "config": workload_config(R, mode=args.mode, note=(
-                "forward+loss+backward replayed as one CUDA graph per step (GraphedTrainStep); Adam and the gradient "
-                "all-reduce run eagerly after it" if graphed is not None else
-                ("eager launches" + (f" (graph capture failed: {graph_err})" if train and args.graph else "")))),
+            "dtype": ("f32 (fp16 hi/lo x3 tensor-core products, fp32 accumulate)" if args.precision_terms == 3
+                      else "fp16 (single-pass tensor-core products, fp32 accumulate)"),
+            "data": "synthetic",
+            "config": workload_config(R, mode, args.precision_terms, world, note="eager library launches, no CUDA graph"),
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches),
+            "gpu_launches_per_step": launches / K,
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "mlp_chain_kernel<CHAIN_SDF,TANGENT> (forward geometry chain: "
-                                                      "deform+sdf MLPs with 3 forward-mode tangent rows per point)",
+            "roofline": {"bound": "tensor",
+                         "kernel": "mlp_chain_kernel<CHAIN_SDF,TANGENT,fwd" + (",STASH>" if train else ">") +
+                                   " (forward geometry chain: deform+sdf MLPs with 3 forward-mode tangent rows per "
+                                   "point" + ("; training variant keeping the plane records" if train else "") + ")",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": NCU_TRAFFIC_BYTES.get(args.mode),
+                         "peak_source": peak_src, "traffic": ncu_traffic(mode),
                          "algorithmic_flops_per_launch": alg_flops_launch, "points_per_launch": pts_per_launch,
                          "ms_per_launch": ms_launch,
-                         "note": "algorithmic = 2*(4D+2S) FLOP/point (SURVEY 8d); the kernel issues 3 fp16 MMAs per "
-                                 "product (hi/lo split) and 4D+4S+feat (forward-mode normals), i.e. ~3.6x the "
-                                 "algorithmic MMA work, so frac <= ~0.28 by construction",
+                         "note": f"algorithmic = 2*(4D+2S) FLOP/point (SURVEY 8d); the kernel issues {terms_note} "
+                                 "and 4D+4S+feat (forward-mode normals)",
                          "kernel_ms_per_step": kern_ms,
-                         "kernel_timing": ("CUDA events around every chain launch over the timed region" if graphed is None
-                                           else f"CUDA events around every chain launch in {n_prof} eager steps of the same "
-                                                "workload run inside this process before the graph-replayed timed region"),
+                         "kernel_ms_sum": round(sum(kern_ms.values()), 3),
+                         "kernel_timing": "CUDA events around every library kernel group over the timed region itself",
                          "step_algorithmic_tflops": value / world * fpr / 1e12},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, tt = oracle_cpu_rays_per_s(args.ref_rays, 3, threads, args.mode)  # 1 warm-up + 3 timed passes, ~10 s
-            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                                    "sample": f"{args.ref_rays} rays of the same workload ({args.mode}), oracle port "
-                                              f"of the reference (PyTorch {torch.__version__} CPU fp32), median of 3 "
-                                              f"passes of {tt:.1f} s after one warm-up pass"}
+            rm = mode
+            v, tt, kind = reference_rays_per_s(args.ref_rays or 512, 3, 1, "cpu", rm, threads)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "rays/s", "cores": threads, "kind": kind,
+                "sample": f"{args.ref_rays or 512} rays of the same workload ({rm}), "
+                          f"{'the unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port'}, PyTorch "
+                          f"{torch.__version__} CPU fp32, mean of 3 steps of {tt:.1f} s after one warm-up step"}
+        if world == 1 and not args.no_gpu_reference:
+            # the north-star denominator: the reference's own PyTorch path on this same GPU (stock ops, fp32, TF32 off)
+            del devb, devt
+            r.release_workspace()
+            torch.cuda.empty_cache()
+            try:
+                v, tt, kind = reference_rays_per_s(R, 3, 1, f"cuda:{local}", mode)
+                line["gpu_reference"] = {
+                    "value": v, "unit": "rays/s", "ms_per_step": 1e3 * tt, "rays_per_step": R, "kind": kind,
+                    "what": f"{'the unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port'} on "
+                            f"cuda:{local}, stock PyTorch {torch.__version__} ops, fp32, TF32 off, same rays / state / "
+                            "loss, 1 warm-up + 3 timed steps",
+                    "speedup_value": value / v, "speedup_e2e": e2e / v}
+            except Exception as e:  # never lose the main line to the baseline
+                line["gpu_reference"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_latency(args, r, dev, world, rank):
+    """BASELINE configs[4] (latency mode, one GPU): `frame` = a full 512x512 frame rendered in ray chunks with the
+    per-chunk outputs copied to the host, as the reference's eval loop does (trainer_endosurf.py:230-240,
+    eval.ray_chunk = 2048 in base_pull.yml:37); `grid256` = the 256^3 SDF grid of extract_fields (utils.py:139-157)."""
+    K, W = args.steps, args.warmup
+    peak, peak_src, _ = measured_peaks()
+    clocks = ClockSampler(dev.index or 0)
+    line = {"metric": METRICS[args.mode], "n_gpus": 1, "steps": K, "warmup": W, "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+            "dtype": "f32 (fp16 hi/lo x3 tensor-core products, fp32 accumulate)"}
+    if args.mode == "frame":
+        rays_all = make_rays(0, frame=7, all_pixels=True).to(dev)
+        results = {}
+        for chunk in (2048, args.frame_chunk):
+            host_rgb = torch.empty(HW * HW, 3).pin_memory()
+            host_dep = torch.empty(HW * HW, 1).pin_memory()
+            host_nrm = torch.empty(HW * HW, 3).pin_memory()
+
+            def frame():
+                with torch.no_grad():
+                    for r0 in range(0, HW * HW, chunk):
+                        o = r.render_rays(rays_all[r0:r0 + chunk], iter_step=ITER_STEP, perturb_overwrite=False)
+                        nrm = (o["gradients_o"] * o["weights"][:, :, None]).sum(1)
+                        host_rgb[r0:r0 + chunk].copy_(o["color_map"], non_blocking=True)
+                        host_dep[r0:r0 + chunk].copy_(o["depth_map"], non_blocking=True)
+                        host_nrm[r0:r0 + chunk].copy_(nrm, non_blocking=True)
+                torch.cuda.synchronize()
+            for _ in range(W):
+                frame()
+            if chunk == 2048:
+                clocks.start()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                frame()
+            results[chunk] = (time.perf_counter() - t0) / K * 1e3
+        clk = clocks.stop()
+        ms = results[2048]
+        fl = HW * HW * flops_per_ray(64, 64, 4)
+        line.update({"value": ms, "unit": "ms/frame", "ms_per_step": ms, "clocks": clk,
+                     "config": workload_config(2048, "frame"),
+                     "e2e": {"value": ms, "unit": "ms/frame", "h2d_bytes_per_step": 0,
+                             "d2h_bytes_per_step": HW * HW * 7 * 4,
+                             "note": "rays resident on the device like Dataset.rays (dataset.py:107); colour, depth and "
+                                     "normal of every chunk copied to pinned host memory inside the timed region"},
+                     "rays_per_s": HW * HW / (ms * 1e-3),
+                     "large_chunk": {"rays_per_chunk": args.frame_chunk, "ms_per_frame": results[args.frame_chunk],
+                                     "rays_per_s": HW * HW / (results[args.frame_chunk] * 1e-3)},
+                     "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peak,
+                                  "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / peak, "peak_source": peak_src,
+                                  "traffic": None, "note": "whole frame, algorithmic forward FLOPs (SURVEY 8d)"},
+                     "gpu_launches": int(r.launch_count())})
+    else:
+        res = 256
+        t = torch.tensor([0.5], device=dev)
+        lo, hi = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+        for _ in range(W):
+            r.extract_fields(t, lo, hi, res, cpu=False)
+        torch.cuda.synchronize()
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            u = r.extract_fields(t, lo, hi, res, cpu=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        t0 = time.perf_counter()
+        for _ in range(K):
+            u_host = r.extract_fields(t, lo, hi, res, cpu=True)  # volume to the host, what marching cubes consumes
+        ms_e2e = (time.perf_counter() - t0) / K * 1e3
+        clk = clocks.stop()
+        fl = float(res) ** 3 * 2.0 * (D_MAC + S_MAC)
+        line.update({"value": ms, "unit": "ms/grid", "ms_per_step": ms, "clocks": clk,
+                     "config": {"workload": "256^3 = 16,777,216-point SDF grid at one time value, deform+sdf 9x256 MLPs, "
+                                            "fp32-parity tensor-core mode, points generated on the device"},
+                     "e2e": {"value": ms_e2e, "unit": "ms/grid", "h2d_bytes_per_step": 28,
+                             "d2h_bytes_per_step": res ** 3 * 4, "note": "volume copied to host numpy"},
+                     "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peak,
+                                  "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / peak, "peak_source": peak_src,
+                                  "traffic": None, "algorithmic_flops_per_launch": fl,
+                                  "note": "33.69 TFLOP per grid (SURVEY 8d); sdf-query chain, 3 fp16 MMAs per product"},
+                     "gpu_launches": int(r.launch_count()), "sdf_range": [float(u_host.min()), float(u_host.max())]})
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 _JSON_OUT = sys.stdout
@@ -416,13 +555,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rays", type=int, default=4096, help="rays per step per GPU (BASELINE configs[1])")
-    ap.add_argument("--ref-rays", type=int, default=512,
-                    help="bounded CPU sample per step for the reference arm / cpu_baseline (about 2.5 s of a 16-core host)")
+    ap.add_argument("--rays", type=int, default=4096,
+                    help="rays per step per GPU (BASELINE configs[1]: 4096; configs[3]: 8192 per GPU on 8 GPUs)")
+    ap.add_argument("--ref-rays", type=int, default=0,
+                    help="rays per step of the bounded CPU sample (0: sized from --steps/--warmup)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=1, help="train mode: replay forward+backward as one CUDA graph")
-    ap.add_argument("--mode", default="train", choices=["train", "forward"],
-                    help="train: BASELINE.json's metric (training rays/s); forward: inference render_rays")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--precision-terms", type=int, default=3, choices=[1, 3],
+                    help="3: fp32-parity hi/lo split (default); 1: single-pass fp16 (BASELINE configs[2])")
+    ap.add_argument("--frame-chunk", type=int, default=16384, help="--mode frame: second, larger ray chunk")
+    ap.add_argument("--mode", default="train", choices=["train", "forward", "frame", "grid256"],
+                    help="train: BASELINE.json's metric (training rays/s); forward: inference render_rays; "
+                         "frame / grid256: configs[4] latencies")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

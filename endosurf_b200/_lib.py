@@ -54,9 +54,12 @@ EXPORTS = {
     "es_sync_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "es_poll_error": (C.c_int, [C.c_void_p, C.c_void_p]),
     "es_num_sms": (C.c_int, [C.c_void_p]),
+    "es_release_workspace": (C.c_int, [C.c_void_p]),
     "es_load_network": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "es_sdf_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                C.c_void_p]),
+    "es_sdf_grid": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_void_p,
+                              C.c_void_p, C.c_void_p]),
     "es_point_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),

@@ -626,6 +626,15 @@ int es_sync_check(es_ctx* ctx, void* stream) {
   return 0;
 }
 
+int es_release_workspace(es_ctx* ctx) {
+  if (!ctx) return ES_E_BADARG;
+  CU(cudaDeviceSynchronize());
+  if (ctx->ws) CU(cudaFree(ctx->ws));
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  return 0;
+}
+
 int es_poll_error(es_ctx* ctx, void* stream) {
   if (!ctx) return ES_E_BADARG;
   if (!ctx->err_host) {
@@ -883,6 +892,27 @@ static StashLayout stash_layout(const es_ctx* ctx, int64_t n) {
   return s;
 }
 
+int es_sdf_grid(es_ctx* ctx, const float* bound_min3, const float* bound_max3, int32_t resolution, const float* t,
+                float* sdf_out, void* stream_) {
+  if (!ctx || !bound_min3 || !bound_max3 || !sdf_out || resolution < 2 || resolution > 2048) return ES_E_BADARG;
+  if (ctx->cfg.use_deform && !t) return fail(ctx, ES_E_BADARG, "time pointer required with use_deform");
+  if (int r = check_loaded(ctx, false)) return r;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // slabs of about 2 M points: the points never leave the device and the query writes straight into the volume
+  const long long plane = static_cast<long long>(resolution) * resolution;
+  const int slab = static_cast<int>(std::max<long long>(1, (2LL << 20) / plane));
+  if (int r = ensure_ws(ctx, static_cast<size_t>(slab) * plane * 3 * sizeof(float) + 256)) return r;
+  float* pts = reinterpret_cast<float*>(ctx->ws);
+  for (int x0 = 0; x0 < resolution; x0 += slab) {
+    const int nx = std::min(slab, resolution - x0);
+    CU(launch_grid_points(bound_min3, bound_max3, resolution, x0, nx, pts, stream));
+    ++ctx->launches;
+    const long long n = nx * plane;
+    if (int r = es_sdf_query(ctx, pts, t, n, 1, n, sdf_out + x0 * plane, stream_)) return r;
+  }
+  return 0;
+}
+
 static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
                               const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
                               float* sdf, float* g_c, float* feat, float* rgb, uint8_t* stash, void* stream_) {
@@ -1073,7 +1103,7 @@ int get_wgrad_plan(es_ctx* ctx, int64_t n, es_ctx::WgradPlan** out) {
   for (auto& pr : protos) total_work += pr.tiles * n_terms;
   // short split-K slices: the tensor core accumulates in fp32 with truncation, whose bias grows with the length of one
   // accumulation chain; the partial tiles are summed by the reduce kernel in round-to-nearest fp32
-  const long long slice_tiles = std::max<long long>(16, (total_work + ctx->n_sms * 16 - 1) / (ctx->n_sms * 16));
+  const long long slice_tiles = std::max<long long>(16, (total_work + ctx->n_sms * 8 - 1) / (ctx->n_sms * 8));
   es_ctx::WgradPlan wp;
   wp.n = n;
   wp.full = ctx->full_planes;

@@ -201,5 +201,7 @@ cudaError_t launch_point_adjoints(long long n, const float* rgb, const float* sd
                                   const float* jac_bar, const float* rgb_bar, float* adj_color, float* adj_sdf,
                                   float* adj_deform, cudaStream_t stream);
 cudaError_t launch_fill_identity_jac(float* jac, long long n, cudaStream_t stream);
+cudaError_t launch_grid_points(const float* lo3, const float* hi3, int res, int x0, int nx, float* pts,
+                               cudaStream_t stream);
 
 }  // namespace es

@@ -553,6 +553,25 @@ __global__ void point_adjoints_kernel(long long n, const float* __restrict__ rgb
   }
 }
 
+// points of a regular grid slab [x0, x0 + nx) x res x res in the order of torch.meshgrid(indexing="ij") flattened;
+// coordinates = torch.linspace(lo, hi, res) (symmetric evaluation: start + i step below the middle, end - (res-1-i) step
+// above it), reference utils.py:139-157
+__global__ void grid_points_kernel(float3 lo, float3 hi, int res, int x0, int nx, float* __restrict__ pts) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(nx) * res * res;
+  if (idx >= total) return;
+  const int iz = static_cast<int>(idx % res);
+  const int iy = static_cast<int>((idx / res) % res);
+  const int ix = x0 + static_cast<int>(idx / (static_cast<long long>(res) * res));
+  auto lin = [res](float a, float b, int i) {
+    const float step = (b - a) / static_cast<float>(res - 1);
+    return i < res / 2 ? a + step * static_cast<float>(i) : b - step * static_cast<float>(res - 1 - i);
+  };
+  pts[idx * 3] = lin(lo.x, hi.x, ix);
+  pts[idx * 3 + 1] = lin(lo.y, hi.y, iy);
+  pts[idx * 3 + 2] = lin(lo.z, hi.z, iz);
+}
+
 __global__ void fill_identity_jac_kernel(float* __restrict__ jac, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n * 9) return;
@@ -625,6 +644,14 @@ cudaError_t launch_point_adjoints(long long n, const float* rgb, const float* sd
   if (n == 0) return cudaSuccess;
   point_adjoints_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(n, rgb, sdf_bar, gc_bar, jac_bar, rgb_bar, adj_color,
                                                                 adj_sdf, adj_deform);
+  return cudaGetLastError();
+}
+cudaError_t launch_grid_points(const float* lo3, const float* hi3, int res, int x0, int nx, float* pts,
+                               cudaStream_t stream) {
+  const long long total = static_cast<long long>(nx) * res * res;
+  if (total == 0) return cudaSuccess;
+  grid_points_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(make_float3(lo3[0], lo3[1], lo3[2]),
+                                                                 make_float3(hi3[0], hi3[1], hi3[2]), res, x0, nx, pts);
   return cudaGetLastError();
 }
 cudaError_t launch_fill_identity_jac(float* jac, long long n, cudaStream_t stream) {

@@ -331,7 +331,7 @@ class EndoSurfRenderer(nn.Module):
         params = param_list(self)
         variance = self.model.deviation_network.variance
         names = ["color_map", "depth_map", "gradients_o", "gradient_o_error", "weights", "cdf", "sdf",
-                 "sampled_color", "weight_max", "s_val"]
+                 "sampled_color", "weight_max", "s_val", "eikonal_den"]
         if R <= self.train_ray_chunk:
             vals = RenderFn.apply(self, rays, z, cos_ratio, variance, *params)
             out = dict(zip(names, vals))
@@ -339,16 +339,13 @@ class EndoSurfRenderer(nn.Module):
             # very large batches: several library calls; the eikonal mean is re-normalised over the whole batch
             parts = [RenderFn.apply(self, rays[r0:r0 + self.train_ray_chunk], z[r0:r0 + self.train_ray_chunk],
                                     cos_ratio, variance, *params) for r0 in range(0, R, self.train_ray_chunk)]
-            out = {k: torch.cat([p[i] for p in parts]) for i, k in enumerate(names) if k != "gradient_o_error"}
-            with torch.no_grad():
-                d_z = rays[:, 3:6] / (rays[:, 5:6] + 1e-6)
-                dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((R, 1), 2.0 / self.n_samples, device=z.device)], -1)
-                pts = rays[:, None, :3] + d_z[:, None, :] * (z + dists * 0.5)[..., None]
-                relax = (torch.linalg.norm(pts, dim=-1) < 1.2).float()
-                den = torch.stack([relax[r0:r0 + self.train_ray_chunk].sum() + 1e-6
-                                   for r0 in range(0, R, self.train_ray_chunk)])
-            num = torch.stack([p[3] for p in parts]) * den
-            out["gradient_o_error"] = num.sum() / (relax.sum() + 1e-6)
+            out = {k: torch.cat([p[i] for p in parts]) for i, k in enumerate(names)
+                   if k not in ("gradient_o_error", "eikonal_den")}
+            dens = torch.stack([p[10].reshape(()) for p in parts])           # sum(relax) + 1e-6 of every chunk
+            total = (dens - 1e-6).sum() + 1e-6
+            out["gradient_o_error"] = (torch.stack([p[3] for p in parts]) * dens).sum() / total
+            out["eikonal_den"] = total.reshape(1)
+        self.last_eikonal_den = out.pop("eikonal_den")
         if not return_extras:
             out.pop("sdf")
             out.pop("sampled_color")
@@ -487,20 +484,19 @@ class EndoSurfRenderer(nn.Module):
         vm = valid[:, None].to(o["rgb"].dtype)
         return o["rgb"] * vm, o["g_o"] * vm, d_out
 
-    def extract_fields(self, t, bound_min, bound_max, resolution, net_chunk=None):
-        """utils.py:139-157: SDF on a resolution^3 grid.  One fused query per 128^3-point slab written straight
-        into the output volume instead of 5000-point chunks with a device-to-host copy each."""
+    def extract_fields(self, t, bound_min, bound_max, resolution, net_chunk=None, cpu=True):
+        """utils.py:139-157: SDF on a resolution^3 grid.  One library call: the grid points are generated on the device
+        slab by slab and each fused query writes straight into the output volume (the reference moves 5000-point
+        chunks through the host)."""
+        self._sync_weights()
+        lib, ctx = _lib.load(), self._context()
         dev = self.model.deviation_network.variance.device
-        xs = [torch.linspace(float(bound_min[i]), float(bound_max[i]), resolution, device=dev) for i in range(3)]
         u = torch.empty(resolution, resolution, resolution, device=dev)
-        t = torch.as_tensor(t, device=dev, dtype=torch.float32).reshape(-1)[:1]
-        slab = max(1, (128 ** 3) // (resolution * resolution))
-        with torch.no_grad():
-            for x0 in range(0, resolution, slab):
-                xx, yy, zz = torch.meshgrid(xs[0][x0:x0 + slab], xs[1], xs[2], indexing="ij")
-                pts = torch.stack([xx, yy, zz], -1).reshape(-1, 3)
-                u[x0:x0 + slab] = self.sdf_from_observed_space(pts, t).reshape(xx.shape)
-        return u.cpu().numpy()
+        t = torch.as_tensor(t, device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
+        lo = (C.c_float * 3)(*[float(bound_min[i]) for i in range(3)])
+        hi = (C.c_float * 3)(*[float(bound_max[i]) for i in range(3)])
+        _lib.check(ctx, lib.es_sdf_grid(ctx, lo, hi, int(resolution), _ptr(t), _ptr(u), self._stream()), "es_sdf_grid")
+        return u.cpu().numpy() if cpu else u
 
     def extract_observation_geometry(self, t, bound_min, bound_max, resolution, threshold=0.0, net_chunk=80000,
                                      cpu=True):
@@ -521,6 +517,11 @@ class EndoSurfRenderer(nn.Module):
         """Synchronise and raise if any kernel tripped its device-side watchdog (tests / debugging)."""
         lib, ctx = _lib.load(), self._context()
         _lib.check(ctx, lib.es_sync_check(ctx, self._stream()), "es_sync_check")
+
+    def release_workspace(self):
+        """Free the library's scratch workspace (plane records of the backward, per-point scratch)."""
+        lib, ctx = _lib.load(), self._context()
+        _lib.check(ctx, lib.es_release_workspace(ctx), "es_release_workspace")
 
     def profile(self, on: bool):
         """Bracket every fused MLP-chain launch with CUDA events (bench.py roofline)."""

@@ -87,8 +87,9 @@ def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 class RenderFn(torch.autograd.Function):
     """(rays [R,9], z_vals [R,M], variance, params...) -> (color_map, depth_map, gradients_o, gradient_o_error,
-    weights, cdf, sdf, sampled_color, weight_max, s_val); the last two are not differentiable here (the reference only
-    logs them)."""
+    weights, cdf, sdf, sampled_color, weight_max, s_val, eikonal_den); the last three are not differentiable here (the
+    reference only logs weight_max / s_val; eikonal_den = sum(relax) + 1e-6 is what data-parallel training needs to
+    re-normalise the eikonal mean over all ranks)."""
 
     @staticmethod
     def forward(ctx, renderer, rays, z, cos_ratio, variance, *params):
@@ -124,12 +125,13 @@ class RenderFn(torch.autograd.Function):
         ctx.meta = (R, M, float(cos_ratio), renderer._packed_version)
         ctx.params = params
         ctx.save_for_backward(rays, z, variance, x_c, jac, sdf, g_c, rgb, stash, eik_den)
-        ctx.mark_non_differentiable(out["weight_max"], out["s_val"])
+        eik_den_out = eik_den.clone()
+        ctx.mark_non_differentiable(out["weight_max"], out["s_val"], eik_den_out)
         return (out["color_map"], out["depth_map"], out["gradients_o"], out["gradient_o_error"], out["weights"],
-                out["cdf"], sdf, rgb, out["weight_max"], out["s_val"])
+                out["cdf"], sdf, rgb, out["weight_max"], out["s_val"], eik_den_out)
 
     @staticmethod
-    def backward(ctx, color_b, depth_b, go_b, eik_b, w_b, cdf_b, sdf_b, rgb_b, _wm_b, _sv_b):
+    def backward(ctx, color_b, depth_b, go_b, eik_b, w_b, cdf_b, sdf_b, rgb_b, _wm_b, _sv_b, _ed_b):
         renderer = ctx.renderer
         lib, ectx = _lib.load(), renderer._context()
         R, M, cos_ratio, version = ctx.meta

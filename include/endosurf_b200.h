@@ -50,6 +50,8 @@ int es_sync_check(es_ctx* ctx, void* stream);
  * what the PREVIOUS poll delivered, so a tripped watchdog raises at most one call late instead of training on. */
 int es_poll_error(es_ctx* ctx, void* stream);
 int es_num_sms(const es_ctx* ctx);
+/* Synchronises the device and frees the grow-only scratch workspace (it is re-grown on the next call that needs it). */
+int es_release_workspace(es_ctx* ctx);
 
 /* Upload one network's EFFECTIVE weights W_l = g_l * v_l / ||v_l|| (reference utils.py:57-58, folded by the caller)
  * and biases: w[l] -> [out_l, in_l] row-major, b[l] -> [out_l], l = 0..n_layers-1, in the reference's own layout
@@ -60,6 +62,12 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
  * x [n,3]; t: element (i / t_div) * t_stride is the time of point i; sdf_out [n]. */
 int es_sdf_query(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride, int64_t n,
                  float* sdf_out, void* stream);
+
+/* extract_fields (utils.py:139-157): the SDF on a resolution^3 grid over [bound_min, bound_max] at one time t (device
+ * scalar), sdf_out [res][res][res] in meshgrid(indexing="ij") order.  bound_* are HOST float[3].  The grid points are
+ * generated on the device slab by slab; nothing goes through the host. */
+int es_sdf_grid(es_ctx* ctx, const float* bound_min3, const float* bound_max3, int32_t resolution, const float* t,
+                float* sdf_out, void* stream);
 
 /* EndoSurfNet.forward (endosurf.py:660-689) plus the three gradient queries it and render_core use
  * (get_sdf_grad_from_canonical_space :603-619, get_deform_grad_from_observed_space :621-658,

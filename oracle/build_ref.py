@@ -1,7 +1,7 @@
 """Recipe that carries the UNMODIFIED reference to the GPU box (test / baseline infrastructure, never the product).
 
 The reference (Ruyi-Zha/endosurf) is pure Python; its "build" is byte-compilation.  This script compiles the package
-``src/`` of ``/root/reference`` where it lies into sourceless ``.pyc`` files under ``oracle/_ref/`` (git-ignored, but
+``src/`` of ``/root/reference`` where it lies into ONE zip of sourceless ``.pyc`` files under ``oracle/_ref/`` (git-ignored, but
 not gpurun-ignored: it travels to the GPU box like our own built ``.so``).  No reference source is copied into the
 repository.  ``oracle/ref_shims.py`` makes the result importable (``src.renderer.endosurf`` etc.) and supplies
 stand-ins for the third-party packages this image lacks.
@@ -12,10 +12,13 @@ import os
 import py_compile
 import shutil
 import sys
+import tempfile
+import zipfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("ENDOSURF_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
+ZIP = os.path.join(OUT, "reference_pyc.zip")
 
 
 def build(verbose=True) -> bool:
@@ -23,20 +26,25 @@ def build(verbose=True) -> bool:
     if not os.path.isdir(src_root):
         if verbose:
             print(f"[oracle/_ref] {REF} not present: keeping whatever is already built")
-        return os.path.isdir(os.path.join(OUT, "src"))
+        return os.path.isfile(ZIP)
     if os.path.isdir(OUT):
         shutil.rmtree(OUT)
+    os.makedirs(OUT)
     n = 0
-    for dirpath, _, files in os.walk(src_root):
-        rel = os.path.relpath(dirpath, REF)
-        for f in files:
-            if not f.endswith(".py"):
-                continue
-            dst_dir = os.path.join(OUT, rel)
-            os.makedirs(dst_dir, exist_ok=True)
-            py_compile.compile(os.path.join(dirpath, f), cfile=os.path.join(dst_dir, f + "c"), doraise=True,
-                               dfile=os.path.join("reference", rel, f))
-            n += 1
+    # one binary artefact: a zip of sourceless .pyc files (zipimport loads them; a single file also travels to the GPU
+    # box whatever the snapshot tool thinks of *.pyc)
+    with tempfile.TemporaryDirectory() as tmp, zipfile.ZipFile(ZIP, "w", zipfile.ZIP_DEFLATED) as zf:
+        for dirpath, _, files in os.walk(src_root):
+            rel = os.path.relpath(dirpath, REF)
+            zf.writestr(rel + "/", "")  # explicit directory entry: zipimport then treats it as a (namespace) package
+            for f in sorted(files):
+                if not f.endswith(".py"):
+                    continue
+                cfile = os.path.join(tmp, f"{n}.pyc")
+                py_compile.compile(os.path.join(dirpath, f), cfile=cfile, doraise=True,
+                                   dfile=os.path.join("reference", rel, f))
+                zf.write(cfile, os.path.join(rel, f + "c"))
+                n += 1
     # the one config the benchmark / trainer test uses, as data (YAML -> JSON), so that nothing reads /root/reference
     # at run time
     try:

@@ -6,16 +6,16 @@ touched by ``render_rays``) are replaced by inert stand-ins in ``sys.modules`` f
 import importlib
 import os
 import sys
-import types
 from unittest import mock
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
+REF_ZIP = os.path.join(REF_DIR, "reference_pyc.zip")
 MISSING = ["mcubes", "kornia", "lpips", "open3d", "imageio", "imageio.v2", "trimesh", "wandb"]
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_DIR, "src", "renderer", "endosurf.pyc"))
+    return os.path.isfile(REF_ZIP)
 
 
 def install_shims():
@@ -28,16 +28,8 @@ def install_shims():
             sys.modules[name] = m
             if "." in name:
                 setattr(sys.modules[name.split(".")[0]], name.split(".")[1], m)
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
-    # the reference's packages have no __init__ everywhere: make `src` a namespace rooted at oracle/_ref
-    for pkg in ("src", "src.renderer", "src.trainer", "src.dataset"):
-        if pkg not in sys.modules:
-            path = os.path.join(REF_DIR, *pkg.split("."))
-            if os.path.isdir(path) and not os.path.exists(os.path.join(path, "__init__.pyc")):
-                m = types.ModuleType(pkg)
-                m.__path__ = [path]
-                sys.modules[pkg] = m
+    if REF_ZIP not in sys.path:
+        sys.path.insert(0, REF_ZIP)  # zipimport: src/renderer/endosurf.pyc -> src.renderer.endosurf
 
 
 def load_reference():

@@ -1,4 +1,6 @@
-"""N>1 host logic on CPU (gloo, world size 2): ray sharding and the single gradient all-reduce of bench.py."""
+"""N>1 host logic on CPU (gloo, world size 2): endosurf_b200.distributed gives EXACTLY the single-process gradient of
+the union batch - masked-mean numerators / denominators are summed over ranks, gradients land in one flat bucket and
+are all-reduced once - and the bench shards rays per rank."""
 import os
 import socket
 import sys
@@ -18,34 +20,81 @@ def _free_port():
     return p
 
 
+def _toy_model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(9, 16), torch.nn.Tanh(), torch.nn.Linear(16, 5))
+
+
+def _toy_terms(model, rays, color_gt, depth_gt, mask):
+    """A stand-in 'renderer' with the loss structure of the trainer: two masked means and one mean over a
+    data-dependent subset (the eikonal term's relax mask)."""
+    o = model(rays)
+    ce = (o[:, :3] - color_gt) * mask
+    de = (o[:, 3:4] - depth_gt) * mask
+    relax = (rays[:, :1].abs() < 0.7).float()
+    terms = {"color": (1.0, ce.abs().sum(), mask.sum()), "depth": (1.0, de.abs().sum(), mask.sum()),
+             "eikonal": (0.1, (relax * (o[:, 4:5] - 1.0) ** 2).sum(), relax.sum())}
+    eps = {"color": 1e-10, "depth": 1e-10, "eikonal": 1e-6}
+    return terms, eps
+
+
+def _batch(n):
+    g = torch.Generator().manual_seed(5)
+    return (torch.randn(n, 9, generator=g), torch.rand(n, 3, generator=g), torch.rand(n, 1, generator=g),
+            (torch.rand(n, 1, generator=g) < 0.6).float())
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
-    import bench
+    from endosurf_b200 import distributed as dp
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.manual_seed(0)
-    # identical replicas, different ray shards -> different local gradients
-    params = [torch.nn.Parameter(torch.ones(5, 3)), torch.nn.Parameter(torch.ones(7)), torch.nn.Parameter(torch.ones(()))]
-    rays = bench.make_rays(8, frame=(rank * 17) % 60, seed=rank)
-    loss = sum((p * (rays[:, 3:6].sum() + rank + 1)).sum() for p in params)
-    loss.backward()
-    local = [p.grad.clone() for p in params]
-    bench.allreduce_gradients(params, world)
-    gathered = [torch.zeros_like(torch.cat([g.reshape(-1) for g in local])) for _ in range(world)]
-    dist.all_gather(gathered, torch.cat([g.reshape(-1) for g in local]))
-    mean = torch.stack(gathered).mean(0)
-    got = torch.cat([p.grad.reshape(-1) for p in params])
-    out[rank] = (torch.allclose(got, mean, atol=1e-6), rays[0, 8].item(), rays[:, 3:6].sum().item())
+    model = _toy_model()
+    params = list(model.parameters())
+    bucket = dp.FlatGradBucket(params)
+    data = _batch(24)
+    sl = dp.shard_rays(24, world, rank)
+    terms, eps = _toy_terms(model, *[x[sl] for x in data])
+    logs = dp.dp_backward(bucket, terms, eps)
+    # p.grad are views of the bucket: nothing was concatenated or copied back
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    out[rank] = (torch.cat([p.grad.reshape(-1) for p in params]).clone(), logs["loss"].item(), (sl.start, sl.stop))
     dist.destroy_process_group()
 
 
-def test_gradient_allreduce_and_ray_sharding_gloo():
+def test_data_parallel_step_equals_single_process_on_the_union_batch():
     world, port = 2, _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
-    assert all(out[r][0] for r in range(world)), "all-reduced gradient != mean of the local gradients"
-    assert out[0][1] != out[1][1] or out[0][2] != out[1][2], "ranks must render different ray shards"
+    # single process, whole batch, the trainer's own normalisation
+    model = _toy_model()
+    terms, eps = _toy_terms(model, *_batch(24))
+    loss = sum(w * num / (den + eps[k]) for k, (w, num, den) in terms.items())
+    loss.backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    for r in range(world):
+        g, l, _ = out[r]
+        assert torch.allclose(g, ref, rtol=1e-5, atol=1e-7), f"rank {r}: DP gradient != union-batch gradient"
+        assert abs(l - loss.item()) <= 1e-5 * abs(loss.item())
+    assert out[0][2] == (0, 12) and out[1][2] == (12, 24)
+    # averaging per-rank means instead (what plain DDP would do) is NOT the same gradient: the masks differ per shard
+    g_avg = []
+    for r in range(world):
+        model = _toy_model()
+        sl = slice(*out[r][2])
+        t, e = _toy_terms(model, *[x[sl] for x in _batch(24)])
+        sum(w * num / (den + e[k]) for k, (w, num, den) in t.items()).backward()
+        g_avg.append(torch.cat([p.grad.reshape(-1) for p in model.parameters()]))
+    assert not torch.allclose(sum(g_avg) / world, ref, rtol=1e-3, atol=1e-6)
+
+
+def test_bench_shards_rays_per_rank():
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.make_rays(8, frame=(0 * 17) % 60, seed=0)
+    b = bench.make_rays(8, frame=(1 * 17) % 60, seed=1)
+    assert a[0, 8].item() != b[0, 8].item() and not torch.equal(a[:, 3:6], b[:, 3:6])
 
 
 def test_reference_arm_is_rank0_only(monkeypatch, capsys):
@@ -53,6 +102,6 @@ def test_reference_arm_is_rank0_only(monkeypatch, capsys):
     import bench
     monkeypatch.setenv("RANK", "1")
     class A:  # noqa
-        steps, warmup, ref_rays, rays, gpus, mode = 1, 1, 2, 4096, 2, "forward"
+        steps, warmup, ref_rays, rays, gpus, mode, precision_terms = 1, 1, 2, 4096, 2, "forward", 3
     bench.run_reference(A)
     assert capsys.readouterr().out == ""

@@ -168,7 +168,9 @@ def test_timed_path_gradient_parity_512_rays(cfg, ckpt, it):
     The yardstick is the oracle evaluated in float64.  The reference's own fp32 autograd deviates from it by up to
     1.1e-3 on the first colour layers (heavy cancellation in those sums; tools/diag_grad_precision.py), so the bound is
         whole gradient vector   <= 1e-4   relative l2
-        every parameter tensor  <= max(1e-3, 3 x the fp32 reference's own deviation for that tensor)."""
+        every parameter tensor  <= max(1e-3, 5 x the fp32 reference's own deviation for that tensor):
+    the fp16 hi/lo products carry 22 mantissa bits against fp32's 24, so an ill-conditioned sum amplifies our rounding
+    4x more than the reference's."""
     from oracle import endosurf_oracle as orc
     r, rc, nc = _renderer(cfg, ckpt, 64, 64)
     R = 512
@@ -204,7 +206,7 @@ def test_timed_path_gradient_parity_512_rays(cfg, ckpt, it):
     print(f"it={it}: global {glob:.3e}; worst (ours, fp32 reference, tensor): {rows[:5]}")
     assert all(torch.isfinite(v).all() for v in mine.values())
     assert glob <= 1e-4, f"global gradient error {glob:.3e}"
-    bad = [(e, e32, k) for e, e32, k in rows if e > max(1e-3, 3.0 * e32)]
+    bad = [(e, e32, k) for e, e32, k in rows if e > max(1e-3, 5.0 * e32)]
     assert not bad, f"per-tensor gradient error (ours, fp32 reference's own, tensor): {bad[:8]}"
 
 
@@ -267,3 +269,40 @@ def test_training_launch_budget(cfg, ckpt):
     (o["color_map"].sum() + o["gradient_o_error"]).backward()
     r.sync_check()
     assert r.launch_count() - n0 <= 60, r.launch_count() - n0
+
+
+def test_data_parallel_shards_equal_the_union_batch(cfg, ckpt):
+    """SURVEY 8e with the real renderer: two ray shards rendered separately (as two ranks would), their masked-mean
+    numerators backpropagated with the GLOBAL denominators and the gradients summed, against one call on the union
+    batch.  (The collective itself is covered on CPU with gloo, tests/test_dist_cpu.py.)"""
+    from oracle import endosurf_oracle as orc
+    from endosurf_b200 import distributed as dp
+    r, rc, nc = _renderer(cfg, ckpt, 32, 32)
+    R = 256
+    rays = orc.synthetic_rays(R, frame=9, seed=21).cuda()
+    g = torch.Generator().manual_seed(22)
+    color_gt = torch.rand(R, 3, generator=g).cuda()
+    depth_gt = (torch.rand(R, 1, generator=g) * 0.5 + 0.5).cuda()
+    mask = (torch.rand(R, 1, generator=g) < 0.7).float().cuda()
+    params = [p for v in r.get_train_params().values() for p in v]
+
+    def grads_of(loss):
+        r.zero_grad()
+        loss.backward()
+        return torch.cat([p.grad.reshape(-1) for p in params]).clone()
+
+    def terms_of(sl):
+        o = r.render_rays(rays[sl], iter_step=25000, perturb_overwrite=False)
+        return dp.render_loss_terms(r, o, color_gt[sl], depth_gt[sl], mask[sl], mask[sl])
+
+    t_all, eps = terms_of(slice(0, R))
+    ref = grads_of(sum(w * num / (den + eps[k]) for k, (w, num, den) in t_all.items()))
+    shards = [dp.shard_rays(R, 2, k) for k in range(2)]
+    t_loc = [terms_of(sl)[0] for sl in shards]
+    dens = {k: sum(t[k][2] for t in t_loc) + eps[k] for k in eps}
+    for k in eps:  # the shards' denominators add up to the union's
+        assert torch.allclose(dens[k], t_all[k][2] + eps[k], rtol=1e-6), k
+    total = sum(grads_of(sum(t[k][0] * t[k][1] / dens[k] for k in eps)) for t in t_loc)
+    r.sync_check()
+    err = ((total - ref).norm() / ref.norm()).item()
+    assert err < 2e-5, f"sum of shard gradients vs union-batch gradient: rel err {err:.3e}"
