@@ -668,64 +668,98 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
   const int Ld = ctx->cfg.use_deform ? static_cast<int>(ctx->plan[ES_NET_DEFORM].packs.size()) : 0;
   uint8_t* units = net == ES_NET_COLOR ? ctx->color_units : ctx->geom_units;
   float* bias = net == ES_NET_COLOR ? ctx->color_bias : ctx->geom_bias + (net == ES_NET_SDF ? Ld * HID : 0);
+  for (int l = 0; l < L; ++l)
+    if (!w[l] || !b[l]) return fail(ctx, ES_E_BADARG, "null layer pointer");
+  PackJobs jobs{};
+  constexpr int kMaxJobs = static_cast<int>(sizeof(jobs.j) / sizeof(jobs.j[0]));
+  bool overflow = false;
+  auto add = [&](const PackJob& j) {
+    if (jobs.n < kMaxJobs) jobs.j[jobs.n++] = j;
+    else overflow = true;
+  };
+  auto copy = [&](const float* src, float* dst, int n) {
+    PackJob j{};
+    j.kind = PACK_COPY;
+    j.w = src;
+    j.dst = dst;
+    j.n_copy = n;
+    add(j);
+  };
+  // forward units + biases of the MMA layers
   for (size_t l = 0; l < P.packs.size(); ++l) {
     const LayerPack& K = P.packs[l];
-    if (!w[l] || !b[l]) return fail(ctx, ES_E_BADARG, "null layer pointer");
-    CU(launch_pack_layer(w[l] + static_cast<size_t>(K.row_off) * K.n_in, K.n_out, K.n_in, K.colmap_dev, K.k_total,
-                         K.scale, units + static_cast<size_t>(K.unit_off) * UNIT_BYTES, stream));
-    ++ctx->launches;
-    if (!(net == ES_NET_SDF && static_cast<int>(l) == L - 1))
-      CU(cudaMemcpyAsync(bias + l * HID, b[l], K.n_out * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    PackJob j{};
+    j.kind = PACK_FORWARD;
+    j.w = w[l] + static_cast<size_t>(K.row_off) * K.n_in;
+    j.n_out = K.n_out;
+    j.n_in = K.n_in;
+    j.cols = K.colmap_dev;
+    j.k_total = K.k_total;
+    j.scale = K.scale;
+    j.units = units + static_cast<size_t>(K.unit_off) * UNIT_BYTES;
+    add(j);
+    if (!(net == ES_NET_SDF && static_cast<int>(l) == L - 1)) copy(b[l], bias + l * HID, K.n_out);
   }
   // output layers kept in fp32 for the epilogue dot products
   const float* wl = w[L - 1];
   const float* bl = b[L - 1];
-  if (!wl || !bl) return fail(ctx, ES_E_BADARG, "null output layer pointer");
   if (net == ES_NET_DEFORM) {
-    CU(cudaMemcpyAsync(ctx->small + SM_DEFORM_W, wl, 3 * HID * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    CU(cudaMemcpyAsync(ctx->small + SM_DEFORM_B, bl, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    copy(wl, ctx->small + SM_DEFORM_W, 3 * HID);
+    copy(bl, ctx->small + SM_DEFORM_B, 3);
   } else if (net == ES_NET_SDF) {
-    CU(cudaMemcpyAsync(ctx->small + SM_SDF_W, wl, HID * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    CU(cudaMemcpyAsync(ctx->small + SM_SDF_B, bl, sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    CU(cudaMemcpyAsync(ctx->small + SM_FEAT_B, bl + 1, HID * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    copy(wl, ctx->small + SM_SDF_W, HID);
+    copy(bl, ctx->small + SM_SDF_B, 1);
+    copy(bl + 1, ctx->small + SM_FEAT_B, HID);
   } else {
-    CU(cudaMemcpyAsync(ctx->small + SM_COLOR_W, wl, 3 * HID * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    CU(cudaMemcpyAsync(ctx->small + SM_COLOR_B, bl, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    copy(wl, ctx->small + SM_COLOR_W, 3 * HID);
+    copy(bl, ctx->small + SM_COLOR_B, 3);
   }
   // transposed units for the reverse (training) chains
+  const float inv_sqrt2 = static_cast<float>(1.0 / std::sqrt(2.0));
+  const int skip = ctx->cfg.skip_layer;
   {
-    const float inv_sqrt2 = static_cast<float>(1.0 / std::sqrt(2.0));
-    const int skip = ctx->cfg.skip_layer;
     uint8_t* ru = ctx->rev_units[net];
     int r = 0;
-    if (net == ES_NET_SDF) {
-      CU(launch_pack_layer_T(w[L - 1] + P.in_dims[L - 1], HID, P.in_dims[L - 1], HID, 1.f,
-                             ru + static_cast<size_t>(r++) * 16 * UNIT_BYTES, stream));
-      ++ctx->launches;
-    }
-    for (int m = L - 2; m >= 1; --m) {
-      CU(launch_pack_layer_T(w[m], P.out_dims[m], P.in_dims[m], P.out_dims[m - 1], m == skip ? inv_sqrt2 : 1.f,
-                             ru + static_cast<size_t>(r++) * 16 * UNIT_BYTES, stream));
-      ++ctx->launches;
-    }
+    auto transposed = [&](const float* src, int k_valid, int stride, int n_valid, float scale) {
+      PackJob j{};
+      j.kind = PACK_TRANSPOSED;
+      j.w = src;
+      j.n_out = k_valid;
+      j.n_in = stride;
+      j.n_valid = n_valid;
+      j.n_mma = HID;
+      j.scale = scale;
+      j.units = ru + static_cast<size_t>(r++) * 16 * UNIT_BYTES;
+      add(j);
+    };
+    if (net == ES_NET_SDF) transposed(w[L - 1] + P.in_dims[L - 1], HID, P.in_dims[L - 1], HID, 1.f);
+    for (int m = L - 2; m >= 1; --m)
+      transposed(w[m], P.out_dims[m], P.in_dims[m], P.out_dims[m - 1], m == skip ? inv_sqrt2 : 1.f);
   }
   // operands of the input-adjoint launches: the network-input columns of W_0 and of W_skip / sqrt 2
   if (net != ES_NET_DEFORM) {
-    const float inv_sqrt2 = static_cast<float>(1.0 / std::sqrt(2.0));
-    const int skip = ctx->cfg.skip_layer;
     for (int k = (net == ES_NET_SDF ? 0 : 1); k <= (net == ES_NET_SDF ? 0 : 2); ++k) {
       const int n_mma = ctx->prog_inadj[k].n_mma;
       const size_t ub = static_cast<size_t>(n_mma) * SUB_K * 2;
-      CU(launch_pack_inadj(w[0], P.out_dims[0], P.in_dims[0], ctx->inadj_cols_dev[k], n_mma, 1.f,
-                           ctx->inadj_units[k], stream));
-      ++ctx->launches;
-      if (skip > 0 && skip < L - 1) {
-        CU(launch_pack_inadj(w[skip], P.out_dims[skip], P.in_dims[skip], ctx->inadj_cols_dev[k] + n_mma, n_mma,
-                             inv_sqrt2, ctx->inadj_units[k] + 16 * ub, stream));
-        ++ctx->launches;
+      for (int which = 0; which < 2; ++which) {
+        if (which == 1 && !(skip > 0 && skip < L - 1)) break;
+        const int m = which ? skip : 0;
+        PackJob j{};
+        j.kind = PACK_TRANSPOSED;
+        j.w = w[m];
+        j.n_out = P.out_dims[m];
+        j.n_in = P.in_dims[m];
+        j.cols = ctx->inadj_cols_dev[k] + which * n_mma;
+        j.n_mma = n_mma;
+        j.scale = which ? inv_sqrt2 : 1.f;
+        j.units = ctx->inadj_units[k] + static_cast<size_t>(which) * 16 * ub;
+        add(j);
       }
     }
   }
+  if (overflow) return fail(ctx, ES_E_UNSUPPORTED, "pack job table too small for this network");
+  CU(launch_pack_jobs(jobs, stream));
+  ++ctx->launches;
   ctx->loaded[net] = true;
   return 0;
 }

@@ -127,6 +127,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx_sa(uint32_t bar_sa, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_sa(uint32_t smem_dst_sa, const void* gsrc, uint32_t bytes, uint32_t bar_sa) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst_sa),
+      "l"(gsrc), "r"(bytes), "r"(bar_sa)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ bulk TMA copy shared -> global (non-tensor form)
 // Completion is tracked per issuing thread with bulk async-groups.  The source must have been made visible to the
 // async proxy (fence.proxy.async after the generic-proxy stores, before the barrier that hands the buffer over).

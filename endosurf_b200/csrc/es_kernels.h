@@ -72,19 +72,27 @@ struct MmaBenchCfg {
 };
 cudaError_t launch_mma_bench(const MmaBenchCfg& cfg, int grid, long long* cycles_out, cudaStream_t stream);
 
-// ---- weight packing (es_pack.cu)
-// Gathers columns of an fp32 [n_out, n_in] matrix into the kernel's K order (colmap[k] = source column or -1),
-// scales, zero-pads rows to 256 and K to 32*n_sub, splits into fp16 hi/lo and writes 16 KiB units
-// [hi(sub0), lo(sub0), hi(sub1), lo(sub1), ...] in the canonical no-swizzle K-major UMMA layout.
-cudaError_t launch_pack_layer(const float* w, int n_out, int n_in, const int* colmap_dev, int k_total, float scale,
-                              uint8_t* units_out, cudaStream_t stream);
-// Transposed pack for the reverse chains: B[n][k] = w[k][n] * scale for k < k_valid (forward out-features),
-// n < n_valid (forward in-features kept: the first 256 / 204 columns); K = 256 (16 units).
-cudaError_t launch_pack_layer_T(const float* w, int k_valid, int n_in_stride, int n_valid, float scale,
-                                uint8_t* units_out, cudaStream_t stream);
-
-cudaError_t launch_pack_inadj(const float* w, int k_valid, int n_in_stride, const int* cols_dev, int n_mma, float scale,
-                              uint8_t* units_out, cudaStream_t stream);
+// ---- weight packing (es_pack.cu): one launch per network over a job table
+enum { PACK_FORWARD = 0, PACK_TRANSPOSED = 1, PACK_COPY = 2 };
+struct PackJob {
+  int kind;
+  int n_out, n_in;     // source matrix w [n_out][n_in] (row stride n_in)
+  int k_total;         // PACK_FORWARD: padded K (multiple of 32)
+  int n_mma;           // PACK_TRANSPOSED: N of the operand (256 for the reverse chains)
+  int n_valid;         // PACK_TRANSPOSED without a column table: rows n < n_valid read column n
+  int n_copy;          // PACK_COPY: floats
+  int work, block0;    // filled by launch_pack_jobs
+  float scale;
+  const float* w;
+  const int* cols;     // PACK_FORWARD: [k_total] kernel K order -> source column; PACK_TRANSPOSED: [n_mma] or null
+  uint8_t* units;
+  float* dst;          // PACK_COPY
+};
+struct PackJobs {
+  int n;
+  PackJob j[48];
+};
+cudaError_t launch_pack_jobs(PackJobs& jobs, cudaStream_t stream);
 
 // ---- weight gradients (es_wgrad.cu)
 struct WgradBases {          // plane records of one backward call (the work list holds offsets, so it can be cached)

@@ -282,6 +282,24 @@ __device__ __forceinline__ void copy_plane_row(uint32_t slot_sa, const uint8_t* 
   }
 }
 
+// SRC_PLANE with both halves present: the chunk comes straight from the record by two 16 KiB bulk copies into the ring
+// slot.  One thread issues them and its arrive on the slot's full barrier carries the transaction bytes; the other
+// epilogue warps only arrive.  (Replaces publish_chunk for this chunk.)
+__device__ __forceinline__ void reload_chunk_bulk(const Epi& c, uint32_t slot, const uint8_t* chi, const uint8_t* clo) {
+  const uint32_t bar = c.sm + BAR_A_FULL + 8 * slot;
+  __syncwarp();
+  if (c.lane == 0) {
+    if (c.quad == 0 && c.part == 0) {
+      const uint32_t slot_sa = c.sm + SM_A_OFF + slot * SLOT_BYTES;
+      mbar_arrive_expect_tx_sa(bar, 2 * CHUNK_PLANE_BYTES);
+      tma_bulk_g2s_sa(slot_sa, chi, CHUNK_PLANE_BYTES, bar);
+      tma_bulk_g2s_sa(slot_sa + SLOT_HALF_BYTES, clo, CHUNK_PLANE_BYTES, bar);
+    } else {
+      mbar_arrive_sa(bar);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ encoder chunks
 // Out of line on purpose: the sin/cos tables need many registers and run only 2-3 times per tile; keeping them out of
 // the chunk loop keeps the hot path's register allocation tight.  Writes one row (16 columns of part `part`) of the
@@ -591,6 +609,10 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
                                    ? io.plane_lo + (static_cast<size_t>(tile) * prog.n_plane_lo + prog.plane_lo[ck]) *
                                                        CHUNK_PLANE_BYTES
                                    : nullptr;
+          if (clo) {
+            reload_chunk_bulk(c, slot, chi, clo);
+            continue;
+          }
           copy_plane_row(slot_sa, chi, clo, row_off);
         } else if (src == SRC_PREV) {
           float v[PCOLS];
@@ -1054,6 +1076,10 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
                                      ? io.plane_lo + (static_cast<size_t>(tile) * prog.n_plane_lo + prog.plane_lo[ck]) *
                                                          CHUNK_PLANE_BYTES
                                      : nullptr;
+            if (clo) {
+              reload_chunk_bulk(c, slot, chi, clo);
+              continue;
+            }
             copy_plane_row(slot_sa, chi, clo, 2 * c.part * A_LBO + c.row * 16);
           } else if (src == SRC_ADJ_FEAT) {
 #pragma unroll
