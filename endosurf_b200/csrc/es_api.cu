@@ -96,6 +96,7 @@ struct es_ctx {
   // lo halves the input-adjoint launches need; 1 = every lo plane (3-term weight gradients, exact gates)
   int full_planes = 0;
   int wgrad_lbo = 0, wgrad_sbo = 0;   // debug override of the MN-major descriptor strides (0: built-in)
+  int pair_mode = 0;                  // standard 256-wide chains run on CTA pairs (cta_group::2)
   float scale_target = 1024.f;        // the largest adjoint entering a reverse chain is scaled to about this:
                                       // 64x below the fp16 maximum (conversions saturate), and small adjoints
                                       // stay above the fp16 subnormal floor (tools/diag_grad_precision.py)
@@ -697,6 +698,7 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
     j.k_total = K.k_total;
     j.scale = K.scale;
     j.units = units + static_cast<size_t>(K.unit_off) * UNIT_BYTES;
+    j.pair = ctx->pair_mode;
     add(j);
     if (!(net == ES_NET_SDF && static_cast<int>(l) == L - 1)) copy(b[l], bias + l * HID, K.n_out);
   }
@@ -730,6 +732,7 @@ int es_load_network(es_ctx* ctx, int net, const float* const* w, const float* co
       j.n_mma = HID;
       j.scale = scale;
       j.units = ru + static_cast<size_t>(r++) * 16 * UNIT_BYTES;
+      j.pair = ctx->pair_mode;
       add(j);
     };
     if (net == ES_NET_SDF) transposed(w[L - 1] + P.in_dims[L - 1], HID, P.in_dims[L - 1], HID, 1.f);
@@ -879,7 +882,8 @@ static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const Cha
   io2.debug_flags = ctx->debug_flags;
   es_ctx::Timed t;
   if (int r = timer_begin(ctx, kind, io.n_points, stream, t)) return r;
-  CU(launch_mlp_chain(chain, tangent, ctx->cfg.use_deform != 0, prog, io2, ctx->n_sms, stream, bwd));
+  const bool pair = ctx->pair_mode && kind != K_INADJ;
+  CU(launch_mlp_chain(chain, tangent, pair, prog, io2, ctx->n_sms, stream, bwd));
   return timer_end(ctx, stream, t);
 }
 
@@ -1627,6 +1631,11 @@ int es_debug_set(es_ctx* ctx, int32_t key, int32_t value) {
     case 1: ctx->wgrad_lbo = value; return 0;     // MN-major descriptor strides of the weight-gradient kernel
     case 2: ctx->wgrad_sbo = value; return 0;
     case 3: ctx->scale_target = std::ldexp(1.f, value); return 0;  // adjoint scale target 2^value
+    case 4:  // CTA pairs on/off; the packed weights change layout: the networks must be loaded again
+      ctx->pair_mode = value != 0;
+      ctx->loaded[ES_NET_SDF] = ctx->loaded[ES_NET_COLOR] = false;
+      ctx->loaded[ES_NET_DEFORM] = !ctx->cfg.use_deform;
+      return 0;
     default: return ES_E_BADARG;
   }
 }

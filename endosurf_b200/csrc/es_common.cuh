@@ -261,6 +261,69 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void umma_commit_sa(uint32_t bar_sa) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_sa) : "memory");
 }
+// ------------------------------------------------------------------ CTA pairs (cta_group::2): two CTAs of a cluster
+// on the two SMs of a TPC run ONE M = 256 MMA per instruction - each supplies its own 128 rows of A and half of the
+// N rows of B from the same shared-memory offsets, each receives its own 128 rows of D in its own TMEM - so the
+// shared-memory traffic of the B operand (reads and the weight stream's writes) is halved per SM.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctaid_x() {  // clusters in the grid
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t sa, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(sa), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_sa) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_sa) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result) {  // same warp index in both CTAs of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+template <uint32_t A_HI, uint32_t B_HI>
+__device__ __forceinline__ void umma2_f16_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(A_HI), "n"(B_HI)
+      : "memory");
+}
+// arrives (count 1) on the barrier at this shared-memory offset in BOTH CTAs of the pair when all previously issued
+// tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma2_commit_sa(uint32_t bar_sa) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_sa),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;

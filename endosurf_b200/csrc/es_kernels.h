@@ -53,7 +53,7 @@ struct ChainIO {
   int debug_flags;  // perf experiments only (ES_DEBUG_FLAGS): 1 = no weight copies, 2 = no A stores, 4 = no MMAs
 };
 
-cudaError_t launch_mlp_chain(int chain, bool tangent, bool use_deform, const ChainProg& prog, const ChainIO& io,
+cudaError_t launch_mlp_chain(int chain, bool tangent, bool pair, const ChainProg& prog, const ChainIO& io,
                              int n_sms, cudaStream_t stream, bool bwd = false);
 int mlp_chain_smem_bytes();
 
@@ -81,6 +81,7 @@ struct PackJob {
   int n_mma;           // PACK_TRANSPOSED: N of the operand (256 for the reverse chains)
   int n_valid;         // PACK_TRANSPOSED without a column table: rows n < n_valid read column n
   int n_copy;          // PACK_COPY: floats
+  int pair;            // units in the CTA-pair layout (two contiguous half-row blocks)
   int work, block0;    // filled by launch_pack_jobs
   float scale;
   const float* w;

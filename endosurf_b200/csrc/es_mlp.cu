@@ -56,7 +56,11 @@ constexpr int BAR_W_FULL = BAR_A_EMPTY + 8 * NSLOT;          // [NSTAGE] TMA -> 
 constexpr int BAR_W_EMPTY = BAR_W_FULL + 8 * NSTAGE;         // [NSTAGE] MMA commit -> TMA
 constexpr int BAR_D_FULL = BAR_W_EMPTY + 8 * NSTAGE;         // [2]      MMA commit -> epilogue
 constexpr int BAR_D_EMPTY = BAR_D_FULL + 16;                 // [2]      epilogue -> MMA  (count N_EPI_WARPS)
-constexpr int SM_TMEM_OFF = BAR_D_EMPTY + 16;
+// CTA pairs: arrivals relayed from the peer CTA into the leader's shared memory (count 1 each)
+constexpr int BAR_A_FULL_PEER = BAR_D_EMPTY + 16;            // [NSLOT]
+constexpr int BAR_W_FULL_PEER = BAR_A_FULL_PEER + 8 * NSLOT; // [NSTAGE]
+constexpr int BAR_D_EMPTY_PEER = BAR_W_FULL_PEER + 8 * NSTAGE;  // [2]
+constexpr int SM_TMEM_OFF = BAR_D_EMPTY_PEER + 16;
 constexpr int SM_TOTAL = SM_TMEM_OFF + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KiB per CTA)");
 
@@ -65,6 +69,31 @@ static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KiB per CTA)");
 #else
 #define ES_FLAG(io, bit) false
 #endif
+
+// ------------------------------------------------------------------------------------------------ tile walk
+// Which tiles a CTA processes.  Single CTAs stride over the tiles; the two CTAs of a pair take tiles 2p and 2p + 1 of the
+// pairs p their cluster strides over, and always run the same number of iterations (the odd one out at the end is a
+// ghost tile: every row invalid, nothing read past the records, nothing written).
+struct TileWalk {
+  long long tile0, step, n_iter, n_tiles;
+};
+template <bool PAIR>
+__device__ __forceinline__ TileWalk make_walk(long long n_tiles) {
+  TileWalk w;
+  w.n_tiles = n_tiles;
+  if constexpr (PAIR) {
+    const long long c = cluster_id_x(), C = cluster_nctaid_x();
+    const long long n_pairs = (n_tiles + 1) / 2;
+    w.tile0 = 2 * c + cluster_ctarank();
+    w.step = 2 * C;
+    w.n_iter = c < n_pairs ? (n_pairs - c + C - 1) / C : 0;
+  } else {
+    w.tile0 = blockIdx.x;
+    w.step = gridDim.x;
+    w.n_iter = static_cast<long long>(blockIdx.x) < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  }
+  return w;
+}
 
 // ------------------------------------------------------------------------------------------------ activations
 template <int ACT>
@@ -525,11 +554,13 @@ static __device__ __noinline__ void inadj_chunk(uint32_t taddr, int src, int par
 }
 
 template <int CHAIN, bool BWD, bool STASH>
-__device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const ChainIO& io, Epi& c, long long n_tiles) {
+__device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const ChainIO& io, Epi& c, const TileWalk tw) {
   constexpr bool DUMP = BWD || STASH;
   const float scale = (BWD && io.scale) ? __ldg(io.scale) : 1.f;
   const uint32_t row_off = 2 * c.part * A_LBO + c.row * 16;  // this thread's 16-byte units inside a chunk half
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  long long tile = tw.tile0;
+  for (long long it = 0; it < tw.n_iter; ++it, tile += tw.step) {
+    const long long tile_r = tile < tw.n_tiles ? tile : tw.n_tiles - 1;  // record index that is safe to read
     // ---------------------------------------------------------- row state
     float xc[3] = {0.f, 0.f, 0.f};        // canonical point (after the deform tail / = x without deform)
     float adj[4] = {0.f, 0.f, 0.f, 0.f};  // reverse chains: (o.x, o.y, o.z, r) adjoint of this row's outputs
@@ -549,9 +580,10 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
       for (int i = 0; i < 3; ++i) xc[i] = __ldg(io.x + pt * 3 + i);
     }
     float sdf_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint8_t* gate_tile = BWD ? io.gate_hi + static_cast<size_t>(tile) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
+    const uint8_t* gate_tile =
+        BWD ? io.gate_hi + static_cast<size_t>(tile_r) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
     const uint8_t* gate_tile_lo =
-        (BWD && prog.gate_use_lo) ? io.gate_lo + static_cast<size_t>(tile) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
+        (BWD && prog.gate_use_lo) ? io.gate_lo + static_cast<size_t>(tile_r) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
 
     for (int l = 0; l < prog.n_layers; ++l, ++c.g) {
       const LayerProg& L = prog.layer[l];
@@ -604,9 +636,9 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
           emit_row(row_sa, v);
         } else if (BWD && src == SRC_PLANE) {
           const uint8_t* chi =
-              io.plane_hi + (static_cast<size_t>(tile) * prog.n_plane + L.arg[ck]) * CHUNK_PLANE_BYTES;
+              io.plane_hi + (static_cast<size_t>(tile_r) * prog.n_plane + L.arg[ck]) * CHUNK_PLANE_BYTES;
           const uint8_t* clo = prog.plane_lo[ck] != NO_DUMP
-                                   ? io.plane_lo + (static_cast<size_t>(tile) * prog.n_plane_lo + prog.plane_lo[ck]) *
+                                   ? io.plane_lo + (static_cast<size_t>(tile_r) * prog.n_plane_lo + prog.plane_lo[ck]) *
                                                        CHUNK_PLANE_BYTES
                                    : nullptr;
           if (clo) {
@@ -981,7 +1013,7 @@ static __device__ __noinline__ void tail_frag(Epi c, uint32_t g_layer, int act, 
 }
 
 template <bool BWD, bool STASH>
-__device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const ChainIO& io, Epi& c, long long n_tiles) {
+__device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const ChainIO& io, Epi& c, const TileWalk tw) {
   constexpr bool DUMP = BWD || STASH;
   const int q = c.lane & 3, p = c.lane >> 2;
   const int colq = PCOLS * c.part + 2 * q;                                        // col(0) inside a 64-column block
@@ -990,7 +1022,9 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
   const bool writer = (c.part == 0);
   const float scale = (BWD && io.scale) ? __ldg(io.scale) : 1.f;
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  long long tile = tw.tile0;
+  for (long long it = 0; it < tw.n_iter; ++it, tile += tw.step) {
+    const long long tile_r = tile < tw.n_tiles ? tile : tw.n_tiles - 1;  // record index that is safe to read
     // ---------------------------------------------------------- point state (same for the 4 lanes of a quad)
     const long long p_raw = tile * TILE_PTS_T + 8 * c.quad + p;
     const bool valid = p_raw < io.n_points;
@@ -1001,9 +1035,10 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
       for (int i = 0; i < 3; ++i) xc[i] = __ldg(io.x + pt * 3 + i);
     }
     float sdf_acc[4][1] = {{0.f}, {0.f}, {0.f}, {0.f}};
-    const uint8_t* gate_tile = BWD ? io.gate_hi + static_cast<size_t>(tile) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
+    const uint8_t* gate_tile =
+        BWD ? io.gate_hi + static_cast<size_t>(tile_r) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
     const uint8_t* gate_tile_lo =
-        (BWD && prog.gate_use_lo) ? io.gate_lo + static_cast<size_t>(tile) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
+        (BWD && prog.gate_use_lo) ? io.gate_lo + static_cast<size_t>(tile_r) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
 
     for (int l = 0; l < prog.n_layers; ++l, ++c.g) {
       const LayerProg& L = prog.layer[l];
@@ -1071,9 +1106,9 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
         } else {
           Frag F;
           if (src == SRC_PLANE) {
-            const uint8_t* chi = io.plane_hi + (static_cast<size_t>(tile) * prog.n_plane + blk) * CHUNK_PLANE_BYTES;
+            const uint8_t* chi = io.plane_hi + (static_cast<size_t>(tile_r) * prog.n_plane + blk) * CHUNK_PLANE_BYTES;
             const uint8_t* clo = prog.plane_lo[ck] != NO_DUMP
-                                     ? io.plane_lo + (static_cast<size_t>(tile) * prog.n_plane_lo + prog.plane_lo[ck]) *
+                                     ? io.plane_lo + (static_cast<size_t>(tile_r) * prog.n_plane_lo + prog.plane_lo[ck]) *
                                                          CHUNK_PLANE_BYTES
                                      : nullptr;
             if (clo) {
@@ -1238,7 +1273,7 @@ __device__ __forceinline__ int post_dump_chunks(const ChainProg& prog) {
   return (STASH && prog.post_op == POST_COLOR_TAIL) ? 4 : 0;
 }
 
-template <int CHAIN, bool TANGENT, bool BWD, bool STASH>
+template <int CHAIN, bool TANGENT, bool BWD, bool STASH, bool PAIR>
 __global__ void __launch_bounds__((BWD || STASH) ? N_THREADS_DUMP : N_THREADS, 1)
 mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__ ChainIO io) {
   constexpr bool DUMP = BWD || STASH;
@@ -1248,45 +1283,57 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const uint32_t sm = smem_u32(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM_OFF);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;  // 0 = leader: issues the MMAs of the pair
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_A_FULL) + i, N_EPI_WARPS);  // one elected arrive per epilogue warp
       // slot free = the MMAs that read it have completed (+ the plane-dump warp has read it, training launches)
       mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_A_EMPTY) + i, DUMP ? 2 : 1);
+      mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_A_FULL_PEER) + i, 1);
     }
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_W_FULL) + i, 1);
       mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_W_EMPTY) + i, 1);
+      mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_W_FULL_PEER) + i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_D_FULL) + i, 1);
       mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_D_EMPTY) + i, N_EPI_WARPS);
+      mbar_init(reinterpret_cast<uint64_t*>(smem + BAR_D_EMPTY_PEER) + i, 1);
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc2<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   if constexpr (!BWD) {  // stage every layer's bias (+ the feature-layer bias in row MAXL) in shared memory
     float* bs = reinterpret_cast<float*>(smem + SM_BIAS_OFF);
     for (int i = threadIdx.x; i < prog.n_layers * HID; i += NT) bs[i] = __ldg(prog.bias + i);
     for (int i = threadIdx.x; i < HID; i += NT) bs[MAXL * HID + i] = __ldg(prog.feat_out_b + i);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // both CTAs' barriers and TMEM exist before anything crosses the pair
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int rows_per_tile = TANGENT ? TILE_PTS_T : TILE_ROWS;  // points per tile
   const long long n_tiles = (io.n_points + rows_per_tile - 1) / rows_per_tile;
+  const TileWalk tw = make_walk<PAIR>(n_tiles);
   int* err = io.err;
 
   if (warp < EPI_WARP0) {
     if (warp == 0 && lane == 0) {
       // ============================================================== TMA producer
+      // pair: each CTA streams ITS half of every unit (128 of the 256 weight rows, packed contiguously)
       uint32_t wc = 0;
       const int step = (prog.n_terms == 3) ? 1 : 2;  // single-term mode skips the lo units (odd indices)
       const uint32_t ubytes = static_cast<uint32_t>(prog.unit_bytes);
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint32_t cbytes = PAIR ? ubytes / 2 : ubytes;
+      const uint8_t* src0 = prog.w_units + (PAIR ? rank * cbytes : 0);
+      for (long long it = 0; it < tw.n_iter; ++it) {
         for (int u = 0; u < prog.units_per_tile; u += step) {
           const uint32_t st = wc % NSTAGE;
           mbar_wait_sa(sm + BAR_W_EMPTY + 8 * st, ((wc / NSTAGE) & 1) ^ 1, err, 200);
@@ -1294,14 +1341,13 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           if (ES_FLAG(io, 1) && wc >= NSTAGE) {
             mbar_arrive(full);
           } else {
-            mbar_arrive_expect_tx(full, ubytes);
-            tma_bulk_g2s(smem + SM_W_OFF + st * UNIT_BYTES, prog.w_units + static_cast<size_t>(u) * ubytes, ubytes,
-                         full);
+            mbar_arrive_expect_tx(full, cbytes);
+            tma_bulk_g2s(smem + SM_W_OFF + st * UNIT_BYTES, src0 + static_cast<size_t>(u) * ubytes, cbytes, full);
           }
           ++wc;
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
       // ============================================================== MMA issuer
       // The tensor pipe retires one M128 N256 K16 UMMA every 128 cycles, and this warp shares its SM sub-partition's
       // issue slots with four busy epilogue warps, so the loop must cost only a few instructions per MMA
@@ -1309,13 +1355,16 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       // The WHOLE warp walks the loop, so every value is warp-uniform and lives in uniform registers - no
       // elect/R2UR broadcast sequence in front of each UTCHMMA - and one elected lane issues.  Ring positions are
       // wrapped counters, not divisions.
-      const uint32_t idesc = make_idesc_f16(TILE_ROWS, prog.n_mma);
+      // Pair: the leader's warp issues M = 256 MMAs for both CTAs; what the peer has ready arrives through the *_PEER
+      // barriers (relayed by the peer's otherwise idle warp 1), completions go to both CTAs by multicast commits.
+      const uint32_t idesc = make_idesc_f16(PAIR ? 2 * TILE_ROWS : TILE_ROWS, prog.n_mma);
 #ifdef ES_TRACE
       unsigned tcount = 0;
 #endif
       // descriptors as low words (address field in 16-byte units + LBO); the high words are compile-time constants
       constexpr uint32_t A_HI32 = smem_desc_hi(A_SBO), W_HI32 = smem_desc_hi(B_SBO);
-      const uint32_t b_lbo = static_cast<uint32_t>(prog.n_mma) * 16;  // bytes between K core matrices of a weight unit
+      // bytes between K core matrices of a weight unit = 16 x the weight rows this CTA holds
+      const uint32_t b_lbo = static_cast<uint32_t>(PAIR ? prog.n_mma / 2 : prog.n_mma) * 16;
       const uint32_t a_desc0 = smem_desc_lo(sm + SM_A_OFF, A_LBO);
       const uint32_t w_desc0 = smem_desc_lo(sm + SM_W_OFF, b_lbo);
       constexpr uint32_t A_KS = (2 * A_LBO) >> 4;          // one K=16 step inside a slot plane
@@ -1329,6 +1378,14 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       uint32_t st = 0, w_par = 0;      // weight ring stage and its phase parity
       uint32_t slot = 0, a_par = 0;    // A ring slot and its phase parity
       uint32_t g = 0;                  // global layer counter (accumulator buffer g & 1)
+      auto mma = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
+        if constexpr (PAIR) umma2_f16_ss_lo<A_HI32, W_HI32>(d, a, b, idesc, acc);
+        else umma_f16_ss_lo<A_HI32, W_HI32>(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar_sa) {
+        if constexpr (PAIR) umma2_commit_sa(bar_sa);
+        else umma_commit_sa(bar_sa);
+      };
       // dump-only chunks (training): nothing to multiply, only the slot hand-shake
       auto skip_chunks = [&](int n) {
         for (int i = 0; i < n; ++i) {
@@ -1337,19 +1394,21 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
         }
       };
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (long long it = 0; it < tw.n_iter; ++it) {
         for (int l = 0; l < prog.n_layers; ++l, ++g) {
           const LayerProg& L = prog.layer[l];
           const int n_chunks = L.n_chunks;
           if constexpr (DUMP) skip_chunks(pre_dump_chunks<BWD, STASH>(L));
           const uint32_t d_tmem = tmem_base + (g & 1) * HID;
           mbar_wait_sa(sm + BAR_D_EMPTY + 8 * (g & 1), ((g >> 1) & 1) ^ 1, err, 300);
+          if constexpr (PAIR) mbar_wait_sa(sm + BAR_D_EMPTY_PEER + 8 * (g & 1), (g >> 1) & 1, err, 301);
           tc_fence_after();
           TRACE_MMA(1000 + l);  // MMA: accumulator free, layer l starts
           uint32_t accum = 0;
           for (int ck = 0; ck < n_chunks; ++ck) {
             const int nsub = L.nsub[ck];
             mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 310);
+            if constexpr (PAIR) mbar_wait_sa(sm + BAR_A_FULL_PEER + 8 * slot, a_par, err, 312);
             tc_fence_after();
             TRACE_MMA(2000 + l * 16 + ck);  // MMA: chunk ck of layer l available
             uint32_t a_hi = a_desc0 + slot * (SLOT_BYTES >> 4);
@@ -1357,16 +1416,17 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
               // ---- hi weight unit: A_hi*B_hi and A_lo*B_hi
               {
                 mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 320);
+                if constexpr (PAIR) mbar_wait_sa(sm + BAR_W_FULL_PEER + 8 * st, w_par, err, 322);
                 tc_fence_after();
                 const uint32_t wd = w_desc0 + st * (UNIT_BYTES >> 4);
                 if (leader) {
                   if (do_mma) {
-                    umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi, wd, idesc, accum);
-                    if (three) umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi + A_LO, wd, idesc, 1);
-                    umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
-                    if (three) umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi + A_LO + A_KS, wd + W_KS, idesc, 1);
+                    mma(d_tmem, a_hi, wd, accum);
+                    if (three) mma(d_tmem, a_hi + A_LO, wd, 1);
+                    mma(d_tmem, a_hi + A_KS, wd + W_KS, 1);
+                    if (three) mma(d_tmem, a_hi + A_LO + A_KS, wd + W_KS, 1);
                   }
-                  umma_commit_sa(sm + BAR_W_EMPTY + 8 * st);
+                  commit(sm + BAR_W_EMPTY + 8 * st);
                 }
                 accum = 1;
                 if (++st == NSTAGE) { st = 0; w_par ^= 1; }
@@ -1374,25 +1434,64 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
               // ---- lo weight unit: A_hi*B_lo
               if (three) {
                 mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 321);
+                if constexpr (PAIR) mbar_wait_sa(sm + BAR_W_FULL_PEER + 8 * st, w_par, err, 323);
                 tc_fence_after();
                 const uint32_t wd = w_desc0 + st * (UNIT_BYTES >> 4);
                 if (leader) {
                   if (do_mma) {
-                    umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi, wd, idesc, 1);
-                    umma_f16_ss_lo<A_HI32, W_HI32>(d_tmem, a_hi + A_KS, wd + W_KS, idesc, 1);
+                    mma(d_tmem, a_hi, wd, 1);
+                    mma(d_tmem, a_hi + A_KS, wd + W_KS, 1);
                   }
-                  umma_commit_sa(sm + BAR_W_EMPTY + 8 * st);
+                  commit(sm + BAR_W_EMPTY + 8 * st);
                 }
                 if (++st == NSTAGE) { st = 0; w_par ^= 1; }
               }
             }
-            if (leader) umma_commit_sa(sm + BAR_A_EMPTY + 8 * slot);
+            if (leader) commit(sm + BAR_A_EMPTY + 8 * slot);
             if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
           }
-          if (leader) umma_commit_sa(sm + BAR_D_FULL + 8 * (g & 1));
+          if (leader) commit(sm + BAR_D_FULL + 8 * (g & 1));
           TRACE_MMA(3000 + l);  // MMA: all MMAs of layer l issued
         }
         if constexpr (DUMP) skip_chunks(post_dump_chunks<BWD, STASH>(prog));
+      }
+      __syncwarp();
+    } else if (PAIR && warp == 1) {
+      // ============================================================== relay (peer CTA of a pair)
+      // Walks the waits of the leader's MMA warp in the same order and forwards this CTA's side of each of them
+      // (accumulator released, A chunk published, weight half landed) to the leader's *_PEER barriers.
+      if (lane == 0) {
+        const int step = (prog.n_terms == 3) ? 1 : 2;
+        uint32_t st = 0, w_par = 0, slot = 0, a_par = 0, g = 0;
+        const uint32_t r_a = mapa_u32(sm + BAR_A_FULL_PEER, 0), r_w = mapa_u32(sm + BAR_W_FULL_PEER, 0),
+                       r_d = mapa_u32(sm + BAR_D_EMPTY_PEER, 0);
+        auto skip_chunks = [&](int n) {
+          for (int i = 0; i < n; ++i) {
+            mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 411);
+            mbar_arrive_sa(sm + BAR_A_EMPTY + 8 * slot);
+            if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
+          }
+        };
+        for (long long it = 0; it < tw.n_iter; ++it) {
+          for (int l = 0; l < prog.n_layers; ++l, ++g) {
+            const LayerProg& L = prog.layer[l];
+            if constexpr (DUMP) skip_chunks(pre_dump_chunks<BWD, STASH>(L));
+            mbar_wait_sa(sm + BAR_D_EMPTY + 8 * (g & 1), ((g >> 1) & 1) ^ 1, err, 400);
+            mbar_arrive_cluster(r_d + 8 * (g & 1));
+            for (int ck = 0; ck < L.n_chunks; ++ck) {
+              mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 410);
+              mbar_arrive_cluster(r_a + 8 * slot);
+              if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
+              const int n_units = L.nsub[ck] * (step == 1 ? 2 : 1);
+              for (int u = 0; u < n_units; ++u) {
+                mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 420);
+                mbar_arrive_cluster(r_w + 8 * st);
+                if (++st == NSTAGE) { st = 0; w_par ^= 1; }
+              }
+            }
+          }
+          if constexpr (DUMP) skip_chunks(post_dump_chunks<BWD, STASH>(prog));
+        }
       }
       __syncwarp();
     }
@@ -1407,15 +1506,17 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 500);
         const uint32_t slot_sa = sm + SM_A_OFF + slot * SLOT_BYTES;
         bool any = false;
-        if (idx_hi != NO_DUMP && io.dump_hi) {
-          tma_bulk_s2g(io.dump_hi + (static_cast<size_t>(tile) * prog.n_dump + idx_hi) * CHUNK_PLANE_BYTES, slot_sa,
-                       CHUNK_PLANE_BYTES);
-          any = true;
-        }
-        if (idx_lo != NO_DUMP && io.dump_lo) {
-          tma_bulk_s2g(io.dump_lo + (static_cast<size_t>(tile) * prog.n_dump_lo + idx_lo) * CHUNK_PLANE_BYTES,
-                       slot_sa + SLOT_HALF_BYTES, CHUNK_PLANE_BYTES);
-          any = true;
+        if (tile < tw.n_tiles) {  // (a pair's ghost tile keeps nothing)
+          if (idx_hi != NO_DUMP && io.dump_hi) {
+            tma_bulk_s2g(io.dump_hi + (static_cast<size_t>(tile) * prog.n_dump + idx_hi) * CHUNK_PLANE_BYTES, slot_sa,
+                         CHUNK_PLANE_BYTES);
+            any = true;
+          }
+          if (idx_lo != NO_DUMP && io.dump_lo) {
+            tma_bulk_s2g(io.dump_lo + (static_cast<size_t>(tile) * prog.n_dump_lo + idx_lo) * CHUNK_PLANE_BYTES,
+                         slot_sa + SLOT_HALF_BYTES, CHUNK_PLANE_BYTES);
+            any = true;
+          }
         }
         if (any) {
           tma_bulk_commit();
@@ -1424,7 +1525,8 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         mbar_arrive_sa(sm + BAR_A_EMPTY + 8 * slot);
         if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
       };
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      long long tile = tw.tile0;
+      for (long long it = 0; it < tw.n_iter; ++it, tile += tw.step) {
         for (int l = 0; l < prog.n_layers; ++l) {
           const LayerProg& L = prog.layer[l];
           const int npre = pre_dump_chunks<BWD, STASH>(L);
@@ -1457,46 +1559,76 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
     c.tr = (io.trace != nullptr && warp == EPI_WARP0 && lane == 0 && blockIdx.x == 0);
     c.tcount = 0;
 #endif
-    if constexpr (TANGENT) epilogue_tangent<BWD, STASH>(prog, io, c, n_tiles);
-    else epilogue_plain<CHAIN, BWD, STASH>(prog, io, c, n_tiles);
+    if constexpr (TANGENT) epilogue_tangent<BWD, STASH>(prog, io, c, tw);
+    else epilogue_plain<CHAIN, BWD, STASH>(prog, io, c, tw);
   }
 
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other still depends on it
+  else __syncthreads();
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-template <int CHAIN, bool TANGENT, bool BWD, bool STASH>
-static cudaError_t launch_one(const ChainProg& prog, const ChainIO& io, int n_sms, cudaStream_t stream) {
-  auto kern = mlp_chain_kernel<CHAIN, TANGENT, BWD, STASH>;
+template <int CHAIN, bool TANGENT, bool BWD, bool STASH, bool PAIR>
+static cudaError_t launch_impl(const ChainProg& prog, const ChainIO& io, int n_sms, cudaStream_t stream) {
+  auto kern = mlp_chain_kernel<CHAIN, TANGENT, BWD, STASH, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
   if (e != cudaSuccess) return e;
   const int pts_per_tile = TANGENT ? TILE_PTS_T : TILE_ROWS;
   long long n_tiles = (io.n_points + pts_per_tile - 1) / pts_per_tile;
   if (n_tiles <= 0) return cudaSuccess;
-  int grid = static_cast<int>(n_tiles < n_sms ? n_tiles : n_sms);
-  kern<<<grid, (BWD || STASH) ? N_THREADS_DUMP : N_THREADS, SM_TOTAL, stream>>>(prog, io);
-  return cudaGetLastError();
+  const int threads = (BWD || STASH) ? N_THREADS_DUMP : N_THREADS;
+  if constexpr (PAIR) {
+    const long long n_pairs = (n_tiles + 1) / 2;
+    const int clusters = static_cast<int>(n_pairs < n_sms / 2 ? n_pairs : n_sms / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = SM_TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, prog, io);
+  } else {
+    int grid = static_cast<int>(n_tiles < n_sms ? n_tiles : n_sms);
+    kern<<<grid, threads, SM_TOTAL, stream>>>(prog, io);
+    return cudaGetLastError();
+  }
+}
+template <int CHAIN, bool TANGENT, bool BWD, bool STASH>
+static cudaError_t launch_one(const ChainProg& prog, const ChainIO& io, int n_sms, cudaStream_t stream, bool pair) {
+  return pair ? launch_impl<CHAIN, TANGENT, BWD, STASH, true>(prog, io, n_sms, stream)
+              : launch_impl<CHAIN, TANGENT, BWD, STASH, false>(prog, io, n_sms, stream);
 }
 
-cudaError_t launch_mlp_chain(int chain, bool tangent, bool use_deform, const ChainProg& prog, const ChainIO& io,
+cudaError_t launch_mlp_chain(int chain, bool tangent, bool pair, const ChainProg& prog, const ChainIO& io,
                              int n_sms, cudaStream_t stream, bool bwd) {
-  (void)use_deform;  // the layer program already encodes whether a deformation network is present
+  // pair: CTA pairs (cta_group::2); the weight units must have been packed in the pair layout (es_pack.cu)
   const bool stash = !bwd && io.dump_hi != nullptr;
   if (prog.n_mma < 16 || prog.n_mma > HID || prog.n_mma % 16 != 0 || prog.unit_bytes != prog.n_mma * SUB_K * 2)
     return cudaErrorInvalidValue;
+  if (pair && prog.n_mma != HID) return cudaErrorInvalidValue;
   if (chain == CHAIN_COLOR) {
-    if (bwd) return launch_one<CHAIN_COLOR, false, true, false>(prog, io, n_sms, stream);
-    return stash ? launch_one<CHAIN_COLOR, false, false, true>(prog, io, n_sms, stream)
-                 : launch_one<CHAIN_COLOR, false, false, false>(prog, io, n_sms, stream);
+    if (bwd) return launch_one<CHAIN_COLOR, false, true, false>(prog, io, n_sms, stream, pair);
+    return stash ? launch_one<CHAIN_COLOR, false, false, true>(prog, io, n_sms, stream, pair)
+                 : launch_one<CHAIN_COLOR, false, false, false>(prog, io, n_sms, stream, pair);
   }
   if (chain == CHAIN_SDF) {
-    if (bwd) return tangent ? launch_one<CHAIN_SDF, true, true, false>(prog, io, n_sms, stream) : cudaErrorInvalidValue;
-    if (!tangent) return launch_one<CHAIN_SDF, false, false, false>(prog, io, n_sms, stream);
-    return stash ? launch_one<CHAIN_SDF, true, false, true>(prog, io, n_sms, stream)
-                 : launch_one<CHAIN_SDF, true, false, false>(prog, io, n_sms, stream);
+    if (bwd)
+      return tangent ? launch_one<CHAIN_SDF, true, true, false>(prog, io, n_sms, stream, pair) : cudaErrorInvalidValue;
+    if (!tangent) return launch_one<CHAIN_SDF, false, false, false>(prog, io, n_sms, stream, pair);
+    return stash ? launch_one<CHAIN_SDF, true, false, true>(prog, io, n_sms, stream, pair)
+                 : launch_one<CHAIN_SDF, true, false, false>(prog, io, n_sms, stream, pair);
   }
   return cudaErrorInvalidValue;
 }

@@ -8,6 +8,15 @@
 
 namespace es {
 
+// byte offset of (k-group kg, weight row n) inside a unit of n_rows rows.  Single CTA: [kg][n_rows][8 fp16].  CTA pair:
+// the two halves of the rows are contiguous blocks, [half][kg][n_rows / 2][8 fp16], because each CTA of the pair streams
+// and holds only its half (the B operand of a cta_group::2 MMA is split over the pair along N).
+__device__ __forceinline__ size_t unit_offset(int pair, int n_rows, int kg, int n) {
+  if (!pair) return static_cast<size_t>(kg) * n_rows * 16 + n * 16;
+  const int h = n_rows / 2;
+  return static_cast<size_t>(n / h) * (h * 64) + static_cast<size_t>(kg) * h * 16 + (n % h) * 16;
+}
+
 // forward layer: gather columns of w [n_out, n_in] into the kernel's K order (colmap[k] = source column or -1), scale,
 // zero-pad rows to 256 and K to 32 n_sub; units [hi(sub0), lo(sub0), hi(sub1), ...], each [k-group 0..3][256][8 fp16]
 __device__ __forceinline__ void pack_forward(const PackJob& J, int idx) {
@@ -23,7 +32,7 @@ __device__ __forceinline__ void pack_forward(const PackJob& J, int idx) {
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-  uint8_t* p = J.units + static_cast<size_t>(2 * sb) * UNIT_BYTES + kg * B_LBO + n * 16;
+  uint8_t* p = J.units + static_cast<size_t>(2 * sb) * UNIT_BYTES + unit_offset(J.pair, HID, kg, n);
   *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(p + UNIT_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
@@ -46,7 +55,7 @@ __device__ __forceinline__ void pack_transposed(const PackJob& J, int idx) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
   const size_t ub = static_cast<size_t>(n_mma) * SUB_K * 2;
-  uint8_t* p = J.units + static_cast<size_t>(2 * sb) * ub + static_cast<size_t>(kg) * n_mma * 16 + n * 16;
+  uint8_t* p = J.units + static_cast<size_t>(2 * sb) * ub + unit_offset(J.pair, n_mma, kg, n);
   *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(p + ub) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }

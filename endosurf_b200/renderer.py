@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -173,6 +174,10 @@ def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+# CTA pairs are the default; ES_PAIR=0 selects the single-CTA kernels (A/B comparisons, debugging)
+PAIR_MODE_DEFAULT = os.environ.get("ES_PAIR", "0") != "0"
+
+
 class EndoSurfRenderer(nn.Module):
     """Drop-in for the reference ``EndoSurfRenderer`` (endosurf.py:14-132) backed by the CUDA library."""
 
@@ -230,7 +235,15 @@ class EndoSurfRenderer(nn.Module):
             if rc != 0:
                 raise _lib.EsError(f"es_create failed: {_lib.ES_E.get(rc, rc)}")
             self._ctx = ctx
+            self.set_pair_mode(PAIR_MODE_DEFAULT)
         return self._ctx
+
+    def set_pair_mode(self, on: bool):
+        """Run the 256-wide chains on CTA pairs (tcgen05 cta_group::2: two SMs share every weight unit) or on single
+        CTAs.  The packed weights change layout, so they are handed to the library again on the next call."""
+        lib, ctx = _lib.load(), self._context()
+        _lib.check(ctx, lib.es_debug_set(ctx, 4, int(bool(on))), "es_debug_set(pair)")
+        self._packed_version = None
 
     def __del__(self):
         try:
