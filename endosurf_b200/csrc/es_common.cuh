@@ -290,7 +290,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t sa, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_sa) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_sa) : "memory");
+  // default (cta-scope) semantics as CUTLASS' ClusterBarrier::arrive: a cluster-scope release costs a memory barrier and
+  // an L1 invalidation per arrive (measured: the relay thread then limits the whole pipeline); the data this arrive
+  // announces was published to the async proxy by its writers (fence.proxy.async) before their own local arrives
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_sa) : "memory");
 }
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result) {  // same warp index in both CTAs of the pair

@@ -45,7 +45,7 @@ constexpr int CHUNK_PLANE_BYTES = SLOT_HALF_BYTES;  // one dumped chunk half: [8
 // dynamic shared memory carve-up (byte offsets from the 1024-aligned base)
 constexpr int SM_A_OFF = 0;
 constexpr int SM_W_OFF = SM_A_OFF + NSLOT * SLOT_BYTES;
-constexpr int SM_XCH_OFF = SM_W_OFF + NSTAGE * UNIT_BYTES;
+constexpr int SM_XCH_OFF = SM_W_OFF + NSTAGE * STAGE_BYTES;
 constexpr int SM_XCH_BYTES = NPART * TILE_ROWS * 4 * 4;      // plain: [part][row][4] floats; tangent: [part][pt][<=12]
 constexpr int SM_BIAS_OFF = SM_XCH_OFF + SM_XCH_BYTES;       // [MAXL + 1][256] fp32: every layer's bias + feat bias
 constexpr int SM_BIAS_BYTES = (MAXL + 1) * HID * 4;
@@ -1328,21 +1328,24 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
     if (warp == 0 && lane == 0) {
       // ============================================================== TMA producer
       // pair: each CTA streams ITS half of every unit (128 of the 256 weight rows, packed contiguously)
+      // one ring stage = one 32-wide K sub-block: its hi unit and (3-term mode) its lo unit, adjacent in the stream
       uint32_t wc = 0;
-      const int step = (prog.n_terms == 3) ? 1 : 2;  // single-term mode skips the lo units (odd indices)
+      const bool three = prog.n_terms == 3;
       const uint32_t ubytes = static_cast<uint32_t>(prog.unit_bytes);
       const uint32_t cbytes = PAIR ? ubytes / 2 : ubytes;
       const uint8_t* src0 = prog.w_units + (PAIR ? rank * cbytes : 0);
       for (long long it = 0; it < tw.n_iter; ++it) {
-        for (int u = 0; u < prog.units_per_tile; u += step) {
+        for (int u = 0; u < prog.units_per_tile; u += 2) {
           const uint32_t st = wc % NSTAGE;
           mbar_wait_sa(sm + BAR_W_EMPTY + 8 * st, ((wc / NSTAGE) & 1) ^ 1, err, 200);
           uint64_t* full = reinterpret_cast<uint64_t*>(smem + BAR_W_FULL) + st;
           if (ES_FLAG(io, 1) && wc >= NSTAGE) {
             mbar_arrive(full);
           } else {
-            mbar_arrive_expect_tx(full, cbytes);
-            tma_bulk_g2s(smem + SM_W_OFF + st * UNIT_BYTES, src0 + static_cast<size_t>(u) * ubytes, cbytes, full);
+            mbar_arrive_expect_tx(full, three ? 2 * cbytes : cbytes);
+            uint8_t* dst = smem + SM_W_OFF + st * STAGE_BYTES;
+            tma_bulk_g2s(dst, src0 + static_cast<size_t>(u) * ubytes, cbytes, full);
+            if (three) tma_bulk_g2s(dst + UNIT_BYTES, src0 + static_cast<size_t>(u + 1) * ubytes, cbytes, full);
           }
           ++wc;
         }
@@ -1371,7 +1374,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       constexpr uint32_t A_LO = SLOT_HALF_BYTES >> 4;      // hi plane -> lo plane
       constexpr uint32_t A_SB = (4 * A_LBO) >> 4;          // one 32-wide sub-block
       const uint32_t W_KS = (2 * b_lbo) >> 4;
-      static_assert(((SM_W_OFF + NSTAGE * UNIT_BYTES) >> 4) < 0x4000, "descriptor address field");
+      static_assert(((SM_W_OFF + NSTAGE * STAGE_BYTES) >> 4) < 0x4000, "descriptor address field");
       const bool three = prog.n_terms == 3;
       const bool do_mma = !ES_FLAG(io, 4);
       const bool leader = elect_one_sync();
@@ -1390,6 +1393,8 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       auto skip_chunks = [&](int n) {
         for (int i = 0; i < n; ++i) {
           mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 311);
+          // (the peer relays these chunks too, so that the phases of A_FULL_PEER stay one per ring pass)
+          if constexpr (PAIR) mbar_wait_sa(sm + BAR_A_FULL_PEER + 8 * slot, a_par, err, 313);
           if (leader) mbar_arrive_sa(sm + BAR_A_EMPTY + 8 * slot);
           if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
         }
@@ -1413,39 +1418,26 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
             TRACE_MMA(2000 + l * 16 + ck);  // MMA: chunk ck of layer l available
             uint32_t a_hi = a_desc0 + slot * (SLOT_BYTES >> 4);
             for (int sb = 0; sb < nsub; ++sb, a_hi += A_SB) {
-              // ---- hi weight unit: A_hi*B_hi and A_lo*B_hi
-              {
-                mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 320);
-                if constexpr (PAIR) mbar_wait_sa(sm + BAR_W_FULL_PEER + 8 * st, w_par, err, 322);
-                tc_fence_after();
-                const uint32_t wd = w_desc0 + st * (UNIT_BYTES >> 4);
-                if (leader) {
-                  if (do_mma) {
-                    mma(d_tmem, a_hi, wd, accum);
-                    if (three) mma(d_tmem, a_hi + A_LO, wd, 1);
-                    mma(d_tmem, a_hi + A_KS, wd + W_KS, 1);
-                    if (three) mma(d_tmem, a_hi + A_LO + A_KS, wd + W_KS, 1);
+              // ---- one stage per sub-block: hi unit (A_hi*B_hi, A_lo*B_hi) and lo unit (A_hi*B_lo)
+              mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 320);
+              if constexpr (PAIR) mbar_wait_sa(sm + BAR_W_FULL_PEER + 8 * st, w_par, err, 322);
+              tc_fence_after();
+              const uint32_t wd = w_desc0 + st * (STAGE_BYTES >> 4);
+              if (leader) {
+                if (do_mma) {
+                  mma(d_tmem, a_hi, wd, accum);
+                  if (three) mma(d_tmem, a_hi + A_LO, wd, 1);
+                  mma(d_tmem, a_hi + A_KS, wd + W_KS, 1);
+                  if (three) {
+                    mma(d_tmem, a_hi + A_LO + A_KS, wd + W_KS, 1);
+                    mma(d_tmem, a_hi, wd + (UNIT_BYTES >> 4), 1);
+                    mma(d_tmem, a_hi + A_KS, wd + (UNIT_BYTES >> 4) + W_KS, 1);
                   }
-                  commit(sm + BAR_W_EMPTY + 8 * st);
                 }
-                accum = 1;
-                if (++st == NSTAGE) { st = 0; w_par ^= 1; }
+                commit(sm + BAR_W_EMPTY + 8 * st);
               }
-              // ---- lo weight unit: A_hi*B_lo
-              if (three) {
-                mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 321);
-                if constexpr (PAIR) mbar_wait_sa(sm + BAR_W_FULL_PEER + 8 * st, w_par, err, 323);
-                tc_fence_after();
-                const uint32_t wd = w_desc0 + st * (UNIT_BYTES >> 4);
-                if (leader) {
-                  if (do_mma) {
-                    mma(d_tmem, a_hi, wd, 1);
-                    mma(d_tmem, a_hi + A_KS, wd + W_KS, 1);
-                  }
-                  commit(sm + BAR_W_EMPTY + 8 * st);
-                }
-                if (++st == NSTAGE) { st = 0; w_par ^= 1; }
-              }
+              accum = 1;
+              if (++st == NSTAGE) { st = 0; w_par ^= 1; }
             }
             if (leader) commit(sm + BAR_A_EMPTY + 8 * slot);
             if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
@@ -1461,13 +1453,13 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       // Walks the waits of the leader's MMA warp in the same order and forwards this CTA's side of each of them
       // (accumulator released, A chunk published, weight half landed) to the leader's *_PEER barriers.
       if (lane == 0) {
-        const int step = (prog.n_terms == 3) ? 1 : 2;
         uint32_t st = 0, w_par = 0, slot = 0, a_par = 0, g = 0;
         const uint32_t r_a = mapa_u32(sm + BAR_A_FULL_PEER, 0), r_w = mapa_u32(sm + BAR_W_FULL_PEER, 0),
                        r_d = mapa_u32(sm + BAR_D_EMPTY_PEER, 0);
         auto skip_chunks = [&](int n) {
           for (int i = 0; i < n; ++i) {
             mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 411);
+            mbar_arrive_cluster(r_a + 8 * slot);
             mbar_arrive_sa(sm + BAR_A_EMPTY + 8 * slot);
             if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
           }
@@ -1482,8 +1474,7 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
               mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 410);
               mbar_arrive_cluster(r_a + 8 * slot);
               if (++slot == NSLOT) { slot = 0; a_par ^= 1; }
-              const int n_units = L.nsub[ck] * (step == 1 ? 2 : 1);
-              for (int u = 0; u < n_units; ++u) {
+              for (int u = 0; u < L.nsub[ck]; ++u) {
                 mbar_wait_sa(sm + BAR_W_FULL + 8 * st, w_par, err, 420);
                 mbar_arrive_cluster(r_w + 8 * st);
                 if (++st == NSTAGE) { st = 0; w_par ^= 1; }
@@ -1585,9 +1576,8 @@ static cudaError_t launch_impl(const ChainProg& prog, const ChainIO& io, int n_s
   const int threads = (BWD || STASH) ? N_THREADS_DUMP : N_THREADS;
   if constexpr (PAIR) {
     const long long n_pairs = (n_tiles + 1) / 2;
-    const int clusters = static_cast<int>(n_pairs < n_sms / 2 ? n_pairs : n_sms / 2);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters);
+    cfg.gridDim = dim3(2 * (n_sms / 2));
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = SM_TOTAL;
     cfg.stream = stream;
@@ -1598,6 +1588,17 @@ static cudaError_t launch_impl(const ChainProg& prog, const ChainIO& io, int n_s
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // persistent grid = the clusters that are resident at once: a pair needs both SMs of a TPC, and a part with
+    // harvested SMs has fewer complete TPCs than n_sms / 2 (a second wave would double the kernel time)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      int mc = 0;
+      if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) mc = n_sms / 2;
+      max_clusters = mc < n_sms / 2 ? mc : n_sms / 2;
+      (void)cudaGetLastError();
+    }
+    const int clusters = static_cast<int>(n_pairs < max_clusters ? n_pairs : max_clusters);
+    cfg.gridDim = dim3(2 * clusters);
     return cudaLaunchKernelEx(&cfg, kern, prog, io);
   } else {
     int grid = static_cast<int>(n_tiles < n_sms ? n_tiles : n_sms);

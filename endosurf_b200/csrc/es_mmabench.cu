@@ -131,8 +131,78 @@ mma_bench_kernel(MmaBenchCfg cfg, MmaNoise nz, long long* cycles_out) {
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// CTA-pair variant (ES_MMAB_PAIR=1): the leader of every 2-CTA cluster issues M256 x N x K16 cta_group::2 MMAs back to
+// back; A = 128 rows per CTA, B = N/2 rows per CTA (descriptor strides from cfg, B LBO for the half-row unit).
+__global__ void __launch_bounds__(128, 1)
+mma_bench_pair_kernel(MmaBenchCfg cfg, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 196608);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 196608 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc2<512>(tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0 && cluster_ctarank() == 0) {
+    const uint32_t idesc = make_idesc_f16(256, cfg.n);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 65536;
+    uint32_t ad[4], bd[4];
+    for (int ks = 0; ks < 4; ++ks) {
+      ad[ks] = smem_desc_lo(a0 + ks * cfg.a_kadv, cfg.a_lbo);
+      bd[ks] = smem_desc_lo(b0 + ks * cfg.b_kadv, cfg.b_lbo);
+    }
+    constexpr uint32_t HI = smem_desc_hi(128);
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < cfg.iters; ++it) {
+      const uint32_t d = tmem_base + (it & 1) * 256;
+      umma2_f16_ss_lo<HI, HI>(d, ad[0], bd[0], idesc, 1);
+      umma2_f16_ss_lo<HI, HI>(d, ad[1], bd[1], idesc, 1);
+      umma2_f16_ss_lo<HI, HI>(d, ad[2], bd[2], idesc, 1);
+      umma2_f16_ss_lo<HI, HI>(d, ad[3], bd[3], idesc, 1);
+    }
+    umma2_commit_sa(smem_u32(bar));
+    int err = 0;
+    mbar_wait(bar, 0, &err, 1);
+    cycles_out[blockIdx.x] = clock64() - t0;
+  } else if (threadIdx.x == 0) {
+    int err = 0;
+    mbar_wait(bar, 0, &err, 1);  // the multicast commit reaches the peer as well
+    cycles_out[blockIdx.x] = 0;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2<512>(tmem_base);
+}
+
 cudaError_t launch_mma_bench(const MmaBenchCfg& cfg, int grid, long long* cycles_out, cudaStream_t stream) {
   const int smem = 196608 + 256;
+  if (const char* v = getenv("ES_MMAB_PAIR")) {
+    if (atoi(v)) {
+      cudaError_t e2 = cudaFuncSetAttribute(mma_bench_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e2 != cudaSuccess) return e2;
+      cudaLaunchConfig_t lc{};
+      lc.gridDim = dim3(grid & ~1);
+      lc.blockDim = dim3(128);
+      lc.dynamicSmemBytes = smem;
+      lc.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      lc.attrs = attr;
+      lc.numAttrs = 1;
+      return cudaLaunchKernelEx(&lc, mma_bench_pair_kernel, cfg, cycles_out);
+    }
+  }
   cudaError_t e = cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   MmaNoise nz{0, 0, 0, 0, 0, 0, nullptr};

@@ -16,11 +16,12 @@ constexpr int SLOT_BYTES = 2 * SLOT_HALF_BYTES;           // 32 KiB
 #define ES_NSLOT 3
 #endif
 #ifndef ES_NSTAGE
-#define ES_NSTAGE 6
+#define ES_NSTAGE 3
 #endif
 constexpr int NSLOT = ES_NSLOT;     // A-operand ring slots (32 KiB each)
 constexpr int UNIT_BYTES = HID * SUB_K * 2;               // 16 KiB: 256 x 32 fp16 (hi or lo)
-constexpr int NSTAGE = ES_NSTAGE;  // weight ring stages (16 KiB each): must cover L2 latency x 43 B/clk (>= 6)
+constexpr int STAGE_BYTES = 2 * UNIT_BYTES;                // one weight ring stage: the hi and the lo unit of a 32-wide K sub-block
+constexpr int NSTAGE = ES_NSTAGE;  // weight ring stages (32 KiB each): must cover L2 latency x 43 B/clk (>= 96 KiB)
 // canonical no-swizzle K-major layout: [k-group of 8][row][8 elements]
 constexpr int A_LBO = TILE_ROWS * 16;  // 2048  bytes between K core matrices
 constexpr int A_SBO = 128;             //        bytes between 8-row groups

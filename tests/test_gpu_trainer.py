@@ -17,7 +17,7 @@ from conftest import load_cfg
 pytestmark = pytest.mark.gpu
 
 
-def _trainer(tmp_path, ray_batch=256, ns=16, ni=16):
+def _trainer(tmp_path, ray_batch=256, ns=16, ni=16, reference_renderer=False):
     tmp_path.mkdir(parents=True, exist_ok=True)
     from oracle import ref_shims
     if not ref_shims.available():
@@ -27,6 +27,8 @@ def _trainer(tmp_path, ray_batch=256, ns=16, ni=16):
     te = importlib.import_module("src.trainer.trainer_endosurf")
     from endosurf_b200.harness import patch_reference_trainer
     patch_reference_trainer(te, tb, n_frames=8, hw=(96, 96))
+    if reference_renderer:  # the reference's own renderer (stock PyTorch on the GPU); only the dataset is the stand-in
+        te.EndoSurfRenderer = importlib.import_module("src.renderer.endosurf").EndoSurfRenderer
     base = load_cfg()
     cfg = {
         "exp": {"project_name": "endosurf", "exp_name": "b200_test", "exp_dir": str(tmp_path / "logs")},
@@ -35,7 +37,7 @@ def _trainer(tmp_path, ray_batch=256, ns=16, ni=16):
         "train": {"n_iter": 100, "ray_batch": ray_batch, "mask_guided_ray_sampling": True, "color_loss_weight": 1.0,
                   "depth_loss_weight": 1.0, "sdf_loss_weight": 1.0, "angle_loss_weight": 0.1,
                   "eikonal_loss_weight": 0.1, "surf_neig_loss_weight": 0.1, "surf_neig_rad": 0.1, "resume": False,
-                  "optim": {"lr": 5e-4, "lr_alpha": 0.05, "warm_up_end": 5}, "eval": {"ray_chunk": 2048}},
+                  "optim": {"lr": 5e-4, "lr_alpha": 0.05, "warm_up_end": 50}, "eval": {"ray_chunk": 2048}},
         "net": copy.deepcopy(base["net"]),
         "log": {"summary_writer": {"type": "tensorboard"}, "i_eval": 0, "i_save": 0},
     }
@@ -62,13 +64,9 @@ def test_first_step_losses_match_the_reference_renderer(tmp_path):
     it drives the reference's own renderer (on the GPU, stock PyTorch) or this one, from the same checkpoint, frame,
     rays and jitter (same RNG stream up to the neighbour sampling of surface_neighbour_error)."""
     import endosurf_b200
+    ref, _ = _trainer(tmp_path / "ref", reference_renderer=True)
     ours, te = _trainer(tmp_path / "ours")
     ref_cls = importlib.import_module("src.renderer.endosurf").EndoSurfRenderer
-    te.EndoSurfRenderer = ref_cls
-    try:
-        ref, _ = _trainer(tmp_path / "ref")
-    finally:
-        te.EndoSurfRenderer = endosurf_b200.EndoSurfRenderer
     assert isinstance(ours.renderer, endosurf_b200.EndoSurfRenderer) and isinstance(ref.renderer, ref_cls)
     ours.renderer.load_checkpoint(ref.renderer.save_checkpoint())
     logs = {}
