@@ -423,10 +423,9 @@ __device__ __forceinline__ void load_raw(const Epi& c, int buf, int blk, float (
 //   softplus : sigma = 1 - exp(-100 h_primal)    (h = softplus(z)  =>  sigma(100 z) = 1 - exp(-100 h))
 //              tangent rows: zdotbar_j = sigma * u_j
 //              primal row  : zbar = sigma * u + 100 (1 - sigma) * sum_j hdot_j * u_j      (softplus'' = 100 s (1-s))
-// ghi / glo: the gating chunk's halves at this row's first column of the part (glo may be null: hi only)
-__device__ __forceinline__ void bwd_gate_plain(const uint8_t* ghi, const uint8_t* glo, int act, float (&u)[PCOLS]) {
-  float h[PCOLS];
-  load_planes(ghi, glo, h);
+// h: the gating activations of this row (load_planes), fetched BEFORE the accumulator wait so that the HBM / L2
+// latency of the record hides behind the MMAs that are still draining
+__device__ __forceinline__ void bwd_gate_plain(const float (&h)[PCOLS], int act, float (&u)[PCOLS]) {
   if (act == ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < PCOLS; ++i) u[i] = h[i] > 0.f ? u[i] : 0.f;
@@ -631,8 +630,12 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
               v[i] = adj[0] * __ldg(prog.outer3_w + col0 + i) + adj[1] * __ldg(prog.outer3_w + HID + col0 + i) +
                      adj[2] * __ldg(prog.outer3_w + 2 * HID + col0 + i);
           }
-          const size_t go = static_cast<size_t>(L.gate_base + L.arg[ck]) * CHUNK_PLANE_BYTES + row_off;
-          bwd_gate_plain(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, L.bwd_act, v);
+          {  // (row form: 16 more live registers for an early fetch spill at the 96-register budget - measured slower)
+            float hg[PCOLS];
+            const size_t go = static_cast<size_t>(L.gate_base + L.arg[ck]) * CHUNK_PLANE_BYTES + row_off;
+            load_planes(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, hg);
+            bwd_gate_plain(hg, L.bwd_act, v);
+          }
           emit_row(row_sa, v);
         } else if (BWD && src == SRC_PLANE) {
           const uint8_t* chi =
@@ -712,10 +715,11 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
       wait_d_full(c, c.g - 1);
 #pragma unroll 1
       for (int blk = 0; blk < 4; ++blk, ++c.ac) {
-        float v[PCOLS];
+        float v[PCOLS], hg[PCOLS];
         load_raw(c, (c.g - 1) & 1, blk, v);
         const size_t go = static_cast<size_t>(prog.post_gate_base + blk) * CHUNK_PLANE_BYTES + row_off;
-        bwd_gate_plain(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, prog.post_bwd_act, v);
+        load_planes(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, hg);
+        bwd_gate_plain(hg, prog.post_bwd_act, v);
         const uint32_t slot = claim_slot<true>(c, blk);
         emit_row(c.sm + SM_A_OFF + slot * SLOT_BYTES + row_off, v);
         publish_chunk(c, slot, 950 + blk);
@@ -906,9 +910,7 @@ __device__ __forceinline__ void load_planes_frag(const uint8_t* phi, const uint8
 }
 
 // activation backward on a fragment (see bwd_gate_plain for the formulas); everything is thread-local
-__device__ __forceinline__ void bwd_gate_frag(const uint8_t* ghi, const uint8_t* glo, int act, Frag& U) {
-  Frag H;
-  load_planes_frag(ghi, glo, H);
+__device__ __forceinline__ void bwd_gate_frag(const Frag& H, int act, Frag& U) {
   if (act == ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1129,6 +1131,9 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
             }
             emit_frag(F, slot_sa + frag_off);
           } else {
+            Frag HG;  // gating activations first: their global-memory latency overlaps the accumulator wait
+            const size_t go = static_cast<size_t>(L.gate_base + blk) * CHUNK_PLANE_BYTES + frag_off;
+            load_planes_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, HG);
             if (src == SRC_BWD_PREV) {
               if (!prev_waited) {
                 wait_d_full(c, c.g - 1);
@@ -1165,8 +1170,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
                 for (int i = 0; i < 4; ++i) F.f[s][i] = (a.x * w[0][i] + a.y * w[1][i] + a.z * w[2][i]) * scale;
               }
             }
-            const size_t go = static_cast<size_t>(L.gate_base + blk) * CHUNK_PLANE_BYTES + frag_off;
-            bwd_gate_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, L.bwd_act, F);
+            bwd_gate_frag(HG, L.bwd_act, F);
             emit_frag(F, slot_sa + frag_off);
           }
         }
@@ -1201,13 +1205,18 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
       }
     } else if (BWD && prog.post_op == POST_BWD_DUMP) {
       // adjoint of the first layer's pre-activation: feeds no MMA of this launch, goes out as 4 dump-only chunks
-      wait_d_full(c, c.g - 1);
+      bool waited = false;
 #pragma unroll 1
       for (int blk = 0; blk < 4; ++blk, ++c.ac) {
-        Frag F;
-        load_frag(c.tmem + ((c.g - 1) & 1) * HID + 64 * blk, F);
+        Frag F, HG;
         const size_t go = static_cast<size_t>(prog.post_gate_base + blk) * CHUNK_PLANE_BYTES + frag_off;
-        bwd_gate_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, prog.post_bwd_act, F);
+        load_planes_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, HG);
+        if (!waited) {
+          wait_d_full(c, c.g - 1);
+          waited = true;
+        }
+        load_frag(c.tmem + ((c.g - 1) & 1) * HID + 64 * blk, F);
+        bwd_gate_frag(HG, prog.post_bwd_act, F);
         const uint32_t slot = claim_slot<true>(c, blk);
         emit_frag(F, c.sm + SM_A_OFF + slot * SLOT_BYTES + frag_off);
         publish_chunk(c, slot, 950 + blk);

@@ -1,10 +1,8 @@
 #!/bin/bash
-# Short GPU session: GPU test suite + the default (training) bench.
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 1800 python -m pytest tests -q -m gpu -s -rs 2>&1 | tail -150 > gpurun_out/t_all.log
-timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-reference > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err
-tail -n 6 gpurun_out/t_all.log
+timeout 900 python -m pytest tests/test_gpu_training.py -q -m gpu 2>&1 | tail -5 > gpurun_out/t_train.log; tail -n 3 gpurun_out/t_train.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-reference > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err
 python - <<'PY'
 import json
 j=json.load(open('gpurun_out/bench_train.json'))

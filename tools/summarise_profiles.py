@@ -102,7 +102,7 @@ with open(os.path.join(P, f"{name}_ncu_summary.txt"), "w") as f:
 
     def is_geom(rec, stash):
         k = rec["kernel"]
-        return "mlp_chain_kernel" in k and "(int)0, (bool)1, (bool)0, (bool)" + ("1" if stash else "0") in k
+        return "mlp_chain_kernel<0, 1, 0, " + ("1" if stash else "0") in k
     for mode, recs, stash in (("train", tr, True), ("forward", fw, False)):
         g = [r for r in recs if is_geom(r, stash)]
         if g:
