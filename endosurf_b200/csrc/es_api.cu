@@ -89,6 +89,7 @@ struct es_ctx {
     std::vector<WgradJob> jobs;   // pointers patched per call
     std::vector<int> job_net;     // ES_NET_* of every job
     std::vector<int> job_layer;
+    bool paired = false;          // launch order = (M half 0, M half 1) pairs: run as 2-CTA clusters
     int* colmaps_dev = nullptr;
   };
   std::vector<WgradPlan> wplans;
@@ -97,6 +98,7 @@ struct es_ctx {
   int full_planes = 0;
   int wgrad_lbo = 0, wgrad_sbo = 0;   // debug override of the MN-major descriptor strides (0: built-in)
   int pair_mode = 0;                  // standard 256-wide chains run on CTA pairs (cta_group::2)
+  int wgrad_pairs = 1;                // weight-gradient CTAs of the two M halves share their B tile (cluster multicast)
   float scale_target = 1024.f;        // the largest adjoint entering a reverse chain is scaled to about this:
                                       // 64x below the fp16 maximum (conversions saturate), and small adjoints
                                       // stay above the fp16 subnormal floor (tools/diag_grad_precision.py)
@@ -1189,6 +1191,23 @@ int get_wgrad_plan(es_ctx* ctx, int64_t n, es_ctx::WgradPlan** out) {
     wp.job_net.push_back(pr.net);
     wp.job_layer.push_back(pr.layer);
   }
+  // launch order: the two M halves of the same (layer, N group, slice) side by side, so that they can run as one
+  // cluster that fetches the shared B tile once (items keep their partial-tile slot in `out`)
+  wp.paired = protos.size() % 2 == 0;
+  for (size_t j = 0; wp.paired && j + 1 < protos.size(); j += 2)
+    wp.paired = protos[j].mhalf == 0 && protos[j + 1].mhalf == 1 && protos[j].net == protos[j + 1].net &&
+                protos[j].layer == protos[j + 1].layer && protos[j].b_chunk == protos[j + 1].b_chunk &&
+                wp.jobs[j].n_slices == wp.jobs[j + 1].n_slices;
+  if (wp.paired) {
+    std::vector<WgradItem> launch;
+    launch.reserve(items.size());
+    for (size_t j = 0; j + 1 < protos.size(); j += 2)
+      for (int k = 0; k < wp.jobs[j].n_slices; ++k) {
+        launch.push_back(items[wp.jobs[j].slot0 + k]);
+        launch.push_back(items[wp.jobs[j + 1].slot0 + k]);
+      }
+    items.swap(launch);
+  }
   wp.n_items = static_cast<int>(items.size());
   CU(cudaMalloc(&wp.items_dev, std::max<size_t>(1, items.size()) * sizeof(WgradItem)));
   CU(cudaMalloc(&wp.colmaps_dev, std::max<size_t>(1, colmaps.size()) * sizeof(int)));
@@ -1369,7 +1388,7 @@ int backward_core(es_ctx* ctx, const BwdIn& a, const BwdScratch& s, es_ctx::Wgra
     bases.p[WB_COLOR_LO] = a.stash + sl.color_lo;
     if (int r = timer_begin(ctx, K_WGRAD, n, stream, t)) return r;
     CU(launch_wgrad(wp.items_dev, wp.n_items, bases, s.partial, s.bias_partial, ctx->wgrad_lbo, ctx->wgrad_sbo,
-                    ctx->err_dev, stream));
+                    ctx->err_dev, stream, wp.paired && ctx->wgrad_pairs));
     if (int r = timer_end(ctx, stream, t)) return r;
     WgradJobs jobs{};
     jobs.n = static_cast<int>(wp.jobs.size());
@@ -1613,8 +1632,18 @@ int es_wgrad_probe(es_ctx* ctx, const uint8_t* zbar_rec, const uint8_t* in_rec, 
   WgradBases bases{};
   bases.p[0] = zbar_rec;
   bases.p[1] = in_rec;
+  bool paired = ctx->wgrad_pairs != 0;
+  if (paired) {  // launch order (half 0, half 1) per slice
+    std::vector<WgradItem> launch;
+    const size_t ns = items.size() / 2;
+    for (size_t k = 0; k < ns; ++k) {
+      launch.push_back(items[k]);
+      launch.push_back(items[ns + k]);
+    }
+    CU(cudaMemcpy(items_dev, launch.data(), launch.size() * sizeof(WgradItem), cudaMemcpyHostToDevice));
+  }
   CU(launch_wgrad(items_dev, static_cast<int>(items.size()), bases, partial, bias_partial, ctx->wgrad_lbo,
-                  ctx->wgrad_sbo, ctx->err_dev, stream));
+                  ctx->wgrad_sbo, ctx->err_dev, stream, paired));
   CU(launch_wgrad_reduce(jobs, partial, bias_partial, stream));
   ctx->launches += 2;
   CU(cudaStreamSynchronize(stream));
@@ -1631,6 +1660,7 @@ int es_debug_set(es_ctx* ctx, int32_t key, int32_t value) {
     case 1: ctx->wgrad_lbo = value; return 0;     // MN-major descriptor strides of the weight-gradient kernel
     case 2: ctx->wgrad_sbo = value; return 0;
     case 3: ctx->scale_target = std::ldexp(1.f, value); return 0;  // adjoint scale target 2^value
+    case 5: ctx->wgrad_pairs = value != 0; return 0;
     case 4:  // CTA pairs on/off; the packed weights change layout: the networks must be loaded again
       ctx->pair_mode = value != 0;
       ctx->loaded[ES_NET_SDF] = ctx->loaded[ES_NET_COLOR] = false;

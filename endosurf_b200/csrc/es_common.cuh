@@ -327,6 +327,25 @@ __device__ __forceinline__ void umma2_commit_sa(uint32_t bar_sa) {
       : "memory");
 }
 
+// bulk copy global -> the SAME shared-memory offset of every CTA in `mask` of the cluster; each destination CTA's
+// mbarrier at the same offset receives the complete_tx
+__device__ __forceinline__ void tma_bulk_g2s_mcast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// single-CTA MMAs, completion signalled to the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;

@@ -142,7 +142,7 @@ struct WnLayers {
   WnLayer l[32];
 };
 cudaError_t launch_wgrad(const WgradItem* items_dev, int n_items, const WgradBases& bases, float* partial,
-                         float* bias_partial, int lbo, int sbo, int* err, cudaStream_t stream);
+                         float* bias_partial, int lbo, int sbo, int* err, cudaStream_t stream, bool paired);
 cudaError_t launch_wgrad_reduce(const WgradJobs& jobs, const float* partial, const float* bias_partial,
                                 cudaStream_t stream);
 int smallm_blocks(long long n_tiles, int n_sms);

@@ -42,6 +42,10 @@ __device__ __forceinline__ void umma_f16_desc(uint32_t d_tmem, uint64_t adesc, u
   umma_f16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
 }
 
+// PAIRED: the two M halves of a (layer, N group, tile slice) run as the two CTAs of a cluster.  Each streams its own A
+// tile and HALF of the shared B tile, multicast into both CTAs' stages, so B crosses L2 / HBM once per pair instead of
+// once per CTA (ncu of the unpaired kernel: 58.5 GB of DRAM reads for 40 GB of records).
+template <bool PAIRED>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_kernel(const WgradItem* __restrict__ items, const __grid_constant__ WgradBases bases, float* __restrict__ partial,
              float* __restrict__ bias_partial, int lbo, int sbo, int* err) {
@@ -56,18 +60,21 @@ wgrad_kernel(const WgradItem* __restrict__ items, const __grid_constant__ WgradB
   uint64_t* bar_done = bar_empty + WG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
   const bool bias = it.bias_mode != 0;
+  const uint32_t rank = PAIRED ? cluster_ctarank() : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < WG_STAGES; ++i) {
       mbar_init(bar_full + i, 1);
-      mbar_init(bar_empty + i, bias ? 5 : 1);  // MMA commit (+ one arrive per bias warp)
+      // stage free: this CTA's MMAs are done with it (+ the peer's, whose B half lands here too; + the bias warps)
+      mbar_init(bar_empty + i, (PAIRED ? 2 : 1) + (bias ? 4 : 0));
     }
     mbar_init(bar_done, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIRED) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_tiles = it.tile1 - it.tile0;
@@ -81,8 +88,15 @@ wgrad_kernel(const WgradItem* __restrict__ items, const __grid_constant__ WgradB
         mbar_wait(bar_empty + st, ((i / WG_STAGES) & 1) ^ 1, err, 600);
         mbar_arrive_expect_tx(bar_full + st, WG_A_BYTES + b_bytes);
         const long long t = it.tile0 + i;
-        tma_bulk_g2s(smem + st * WG_STAGE_BYTES, a_ptr + t * it.a_stride, WG_A_BYTES, bar_full + st);
-        tma_bulk_g2s(smem + st * WG_STAGE_BYTES + WG_A_BYTES, b_ptr + t * it.b_stride, b_bytes, bar_full + st);
+        uint8_t* stage = smem + st * WG_STAGE_BYTES;
+        tma_bulk_g2s(stage, a_ptr + t * it.a_stride, WG_A_BYTES, bar_full + st);
+        if constexpr (PAIRED) {
+          const uint32_t half = b_bytes / 2;
+          tma_bulk_g2s_mcast(stage + WG_A_BYTES + rank * half, b_ptr + t * it.b_stride + rank * half, half,
+                             bar_full + st, 3);
+        } else {
+          tma_bulk_g2s(stage + WG_A_BYTES, b_ptr + t * it.b_stride, b_bytes, bar_full + st);
+        }
       }
     }
   } else if (warp == 1) {
@@ -103,7 +117,8 @@ wgrad_kernel(const WgradItem* __restrict__ items, const __grid_constant__ WgradB
                         make_smem_desc(sb + ks * 2 * WG_LBO, lbo, sbo), idesc, accum);
           accum = 1;
         }
-        umma_commit(bar_empty + st);
+        if constexpr (PAIRED) umma_commit_mcast(bar_empty + st, 3);
+        else umma_commit(bar_empty + st);
       }
       __syncwarp();
     }
@@ -172,7 +187,8 @@ wgrad_kernel(const WgradItem* __restrict__ items, const __grid_constant__ WgradB
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIRED) cluster_sync_all();  // the peer may still multicast into this CTA's stages / barriers
+  else __syncthreads();
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
@@ -362,12 +378,34 @@ __global__ void scale_from_amax_kernel(const unsigned int* __restrict__ amax_bit
 
 // ---------------------------------------------------------------------------------------------- launchers
 cudaError_t launch_wgrad(const WgradItem* items_dev, int n_items, const WgradBases& bases, float* partial,
-                         float* bias_partial, int lbo, int sbo, int* err, cudaStream_t stream) {
+                         float* bias_partial, int lbo, int sbo, int* err, cudaStream_t stream, bool paired) {
   if (n_items <= 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+  if (paired) {
+    // items 2k, 2k+1 = the two M halves of one (layer, N group, slice): one cluster
+    if (n_items % 2) return cudaErrorInvalidValue;
+    auto kern = wgrad_kernel<true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_items);
+    cfg.blockDim = dim3(WG_THREADS);
+    cfg.dynamicSmemBytes = WG_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, items_dev, bases, partial, bias_partial, lbo > 0 ? lbo : WG_LBO,
+                              sbo > 0 ? sbo : WG_SBO, err);
+  }
+  auto kern = wgrad_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
   if (e != cudaSuccess) return e;
-  wgrad_kernel<<<n_items, WG_THREADS, WG_SMEM, stream>>>(items_dev, bases, partial, bias_partial,
-                                                         lbo > 0 ? lbo : WG_LBO, sbo > 0 ? sbo : WG_SBO, err);
+  kern<<<n_items, WG_THREADS, WG_SMEM, stream>>>(items_dev, bases, partial, bias_partial, lbo > 0 ? lbo : WG_LBO,
+                                                 sbo > 0 ? sbo : WG_SBO, err);
   return cudaGetLastError();
 }
 cudaError_t launch_wgrad_reduce(const WgradJobs& jobs, const float* partial, const float* bias_partial,

@@ -107,7 +107,9 @@ def test_point_forward_ragged_sizes(cfg, ckpt):
 
 
 def test_up_sample_trace(cfg, ckpt):
-    g = load_npz("render_r32_s32_i32_it25k.npz")
+    """up_sample on the per-step inputs and outputs of the REFERENCE's own up_sample / cat_z_vals chain
+    (tests/golden/make_upsample_golden.py replays endosurf.py:85-110 with the unmodified reference)."""
+    g = load_npz("upsample_ref.npz")
     r = _renderer(cfg, ckpt, 32, 32)
     rays = torch.from_numpy(g["rays"]).cuda()
     for i in range(4):
@@ -115,6 +117,34 @@ def test_up_sample_trace(cfg, ckpt):
         out = r.up_sample(rays[:, :3], rays[:, 3:6], z, sdf, 8, 64 * 2 ** i)
         r.sync_check()
         assert_close(f"new_z step {i}", out, new_z, 2e-5)
+    # the whole chain (coarse z -> 4 x {up_sample, sdf query, sorted merge}) against the reference's final z_vals;
+    # resampling is discontinuous in the coarse sdf, hence the quantile gate (see conftest.assert_close)
+    with torch.no_grad():
+        z_mine = r._sample_z(rays, 25000, False)
+    r.sync_check()
+    assert_close("z_vals after cat_z_vals x4", z_mine, g["z_final"], 1e-4, kink_tol=5e-2, q=0.98)
+    assert (z_mine[:, 1:] >= z_mine[:, :-1]).all()
+
+
+@pytest.mark.parametrize("tag", ["r48_s64_i64_it50k", "r32_nodeform_s32_i32"])
+def test_cta_pair_kernels_match_single_cta(cfg, ckpt, tag):
+    """The CTA-pair variant of the chain kernel (tcgen05 cta_group::2, the two SMs of a TPC share every weight unit)
+    computes the same thing as the single-CTA kernels (same products, same K order): per-sample outputs within 1e-6."""
+    g = load_npz(f"render_{tag}.npz")
+    use_deform = "nodeform" not in tag
+    rays = torch.from_numpy(g["rays"]).cuda()
+    z = torch.from_numpy(g["z_vals"]).cuda()
+    outs = []
+    for pair in (False, True):
+        r = _renderer(cfg, ckpt, int(g["n_samples"]), int(g["n_importance"]), use_deform)
+        r.set_pair_mode(pair)
+        with torch.no_grad():
+            outs.append(r.render_rays(rays, iter_step=int(g["iter_step"]), perturb_overwrite=False, z_vals_override=z,
+                                      return_extras=True))
+        r.sync_check()
+    for k in ["color_map", "depth_map", "weights", "sdf", "sampled_color", "gradients_o"]:
+        assert_close(k + " (pair vs single)", outs[1][k], outs[0][k], 1e-6)
+    assert_close("color_map", outs[1]["color_map"], g["core/color_map"], TOL)
 
 
 CASES = [("r48_s64_i64_it0", True), ("r48_s64_i64_it50k", True), ("r32_s32_i32_it25k", True),

@@ -37,12 +37,15 @@ def _probe(r, zbar, a, bias_mode):
     return out.cpu(), bias.cpu()
 
 
+@pytest.mark.parametrize("paired", [True, False])
 @pytest.mark.parametrize("n_b,tiles,bias_mode", [(4, 7, 1), (1, 3, 2), (2, 1, 0), (3, 10, 2)])
-def test_wgrad_kernel_matches_matmul(cfg, ckpt, n_b, tiles, bias_mode):
+def test_wgrad_kernel_matches_matmul(cfg, ckpt, n_b, tiles, bias_mode, paired):
     """out = zbar^T a over tiles*128 rows; fp16 inputs, fp32 accumulation: exact products, so the only error is the
     summation order."""
     from endosurf_b200 import _lib
     r = _ctx_renderer(cfg, ckpt)
+    # paired: the two M halves run as a 2-CTA cluster sharing the B tile by multicast; unpaired: independent CTAs
+    _lib.load().es_debug_set(r._context(), 5, int(paired))
     g = torch.Generator().manual_seed(7 + n_b)
     rows = tiles * 128
     zbar = (torch.randn(rows, 256, generator=g) * torch.rand(rows, 1, generator=g)).half()
