@@ -406,7 +406,8 @@ def run_ours(args):
             "dtype": ("f32 (fp16 hi/lo x3 tensor-core products, fp32 accumulate)" if args.precision_terms == 3
                       else "fp16 (single-pass tensor-core products, fp32 accumulate)"),
             "data": "synthetic",
-            "config": workload_config(R, mode, args.precision_terms, world, note="eager library launches, no CUDA graph"),
+            "config": workload_config(R, mode, args.precision_terms, world),
+            "launch_mode": "eager library launches, no CUDA graph",
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches),

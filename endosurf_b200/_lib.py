@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libendosurf_b200.so")
+# ES_LIB_PATH: profiling tools load an instrumented variant of the library (endosurf_b200.build --tag=...); the product
+# never sets it
+LIB_PATH = os.environ.get("ES_LIB_PATH") or os.path.join(_HERE, "libendosurf_b200.so")
 
 ES_E = {-1: "ES_E_BADARG", -2: "ES_E_UNSUPPORTED", -3: "ES_E_NOWEIGHTS", -4: "ES_E_DEVICE"}
 

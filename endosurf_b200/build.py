@@ -41,14 +41,17 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, tag: str = "") -> str:
+    """tag: build a variant (ES_NVCC_FLAGS, e.g. -DES_TRACE) into libendosurf_b200_<tag>.so with its own objects, next
+    to the product library (profiling tools load it through ES_LIB_PATH)."""
     nvcc = _nvcc()
+    lib = LIB if not tag else LIB.replace(".so", f"_{tag}.so")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "endosurf_b200.h"))
     objs = []
     for src, extra in SOURCES.items():
         s = os.path.join(CSRC, src)
-        o = os.path.join(CSRC, src.replace(".cu", ".o"))
+        o = os.path.join(CSRC, src.replace(".cu", (f".{tag}" if tag else "") + ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
             cmd = [nvcc, *ARCH, *COMMON, *extra, *os.environ.get("ES_NVCC_FLAGS", "").split(), "-c", s, "-o", o]
@@ -60,13 +63,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError(f"nvcc failed on {src}:\n{log}")
             if verbose:
                 print(log)
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
+    if force or _stale(lib, objs):
+        cmd = [nvcc, *ARCH, "-shared", "-o", lib, *objs, "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    tags = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tag=tags[0] if tags else ""))

@@ -106,6 +106,7 @@ struct es_ctx {
   bool profiling = false;
   int debug_flags = 0;
   long long* trace_dev = nullptr;  // debug pipeline trace buffer (es_debug_trace)
+  int trace_kind = -1;
   struct Timed {
     int kind;
     long long points;
@@ -880,7 +881,7 @@ static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const Cha
   ChainProg prog = prog_in;
   if (bwd || io.dump_hi) apply_plane_mode(ctx, kind, inadj_k, prog);
   ChainIO io2 = io;
-  io2.trace = ctx->trace_dev;
+  io2.trace = (ctx->trace_kind < 0 || ctx->trace_kind == kind) ? ctx->trace_dev : nullptr;
   io2.debug_flags = ctx->debug_flags;
   es_ctx::Timed t;
   if (int r = timer_begin(ctx, kind, io.n_points, stream, t)) return r;
@@ -1661,6 +1662,7 @@ int es_debug_set(es_ctx* ctx, int32_t key, int32_t value) {
     case 2: ctx->wgrad_sbo = value; return 0;
     case 3: ctx->scale_target = std::ldexp(1.f, value); return 0;  // adjoint scale target 2^value
     case 5: ctx->wgrad_pairs = value != 0; return 0;
+    case 6: ctx->trace_kind = value; return 0;    // ES_TRACE builds: only launches of this kind write the trace (-1: all)
     case 4:  // CTA pairs on/off; the packed weights change layout: the networks must be loaded again
       ctx->pair_mode = value != 0;
       ctx->loaded[ES_NET_SDF] = ctx->loaded[ES_NET_COLOR] = false;

@@ -64,7 +64,9 @@ constexpr int SM_TMEM_OFF = BAR_D_EMPTY_PEER + 16;
 constexpr int SM_TOTAL = SM_TMEM_OFF + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KiB per CTA)");
 
-#ifdef ES_ABLATE  // perf experiments (ES_DEBUG_FLAGS): 1 = no weight copies, 2 = no A stores, 4 = no MMAs
+#ifdef ES_ABLATE  // perf experiments (ES_DEBUG_FLAGS): 1 = no weight copies, 2 = no A stores, 4 = no MMAs,
+                  // 8 = no L2 gate prefetch (reverse chains), 16 = no plane-record stores (training launches),
+                  // 32 = plane records of every tile land on the CTA's first tile (L2-resident stores)
 #define ES_FLAG(io, bit) (((io).debug_flags & (bit)) != 0)
 #else
 #define ES_FLAG(io, bit) false
@@ -552,6 +554,58 @@ static __device__ __noinline__ void inadj_chunk(uint32_t taddr, int src, int par
   for (int i = 0; i < 10; ++i) xb_out[i] = xb[i];
 }
 
+// ------------------------------------------------------------------------------------------------ gate prefetch
+// The reverse chains gate every accumulator chunk with the forward record of the same rows.  Loaded on demand those
+// words come from HBM (1500-2500 cycles, pipeline trace of round 2: 3200 cycles per chunk against 1536 cycles of MMAs):
+// every thread therefore prefetches the lines it will read one layer ahead into L2 (no registers, no shared memory).
+__device__ __forceinline__ bool is_gate_src(int src) { return src == SRC_BWD_PREV || src == SRC_BWD_OUTER3; }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// off = the thread's offset inside a chunk half (fragment form: frag_off, ns = streams fetched; row form: row_off, ns = 0)
+__device__ __forceinline__ void prefetch_chunk_gate(const uint8_t* chunk, int ns) {
+  if (ns == 0) {  // row form: load_planes
+#pragma unroll
+    for (int g = 0; g < PCOLS / 8; ++g) prefetch_l2(chunk + g * A_LBO);
+  } else {        // fragment form: load_planes_frag
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      prefetch_l2(chunk + j * A_LBO);
+      if (ns == 4) {
+#pragma unroll
+        for (int s = 1; s < 4; ++s) prefetch_l2(chunk + j * A_LBO + s * 128);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void prefetch_layer_gates(const uint8_t* gate_tile, const LayerProg& L, uint32_t off,
+                                                     bool frag) {
+  const int ns = frag ? (L.bwd_act == ACT_RELU ? 1 : 4) : 0;
+  for (int ck = 0; ck < L.n_chunks; ++ck) {
+    const int src = L.src[ck];
+    if (src == SRC_BWD_PREV || src == SRC_BWD_OUTER3)
+      prefetch_chunk_gate(gate_tile + static_cast<size_t>(L.gate_base + L.arg[ck]) * CHUNK_PLANE_BYTES + off, ns);
+  }
+}
+// what follows layer l of a reverse chain: layer l + 1, or (after the last layer) the dump-only result chunks of this
+// tile and the first layer of the CTA's next tile
+__device__ __forceinline__ void prefetch_next_gates(const ChainProg& prog, const ChainIO& io, const uint8_t* gate_tile,
+                                                    int l, long long next_tile, long long n_tiles, uint32_t off,
+                                                    bool frag) {
+  if (l + 1 < prog.n_layers) {
+    prefetch_layer_gates(gate_tile, prog.layer[l + 1], off, frag);
+    return;
+  }
+  if (prog.post_op == POST_BWD_DUMP) {
+    const int ns = frag ? (prog.post_bwd_act == ACT_RELU ? 1 : 4) : 0;
+    for (int blk = 0; blk < 4; ++blk)
+      prefetch_chunk_gate(gate_tile + static_cast<size_t>(prog.post_gate_base + blk) * CHUNK_PLANE_BYTES + off, ns);
+  }
+  if (next_tile < n_tiles)
+    prefetch_layer_gates(io.gate_hi + static_cast<size_t>(next_tile) * prog.n_gate * CHUNK_PLANE_BYTES, prog.layer[0],
+                         off, frag);
+}
+
 template <int CHAIN, bool BWD, bool STASH>
 __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const ChainIO& io, Epi& c, const TileWalk tw) {
   constexpr bool DUMP = BWD || STASH;
@@ -591,6 +645,10 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
       const int last_prev = L.last_prev;
       const int n_chunks = L.n_chunks;
       bool prev_waited = false;
+      if constexpr (BWD) {
+        if (io.gate_hi && !ES_FLAG(io, 8))
+          prefetch_next_gates(prog, io, gate_tile, l, tile + tw.step, tw.n_tiles, row_off, false);
+      }
 
       if (!BWD && L.pre_op == PRE_DEFORM_TAIL) {
         // deform output layer (3 x 256, fp32 FFMA) -> x_c = x + delta
@@ -894,9 +952,12 @@ __device__ __forceinline__ void emit_frag(const Frag& F, uint32_t sa) {
 // fragment of a dumped plane chunk (value = hi + lo, plo may be null); pointers at the chunk half + the same
 // per-thread offset as in the ring slot (k-group 2 part, row 32Q + p, byte 4q).  A warp-wide 4-byte load covers 8
 // consecutive rows x 16 bytes = one full 128-byte line.
-__device__ __forceinline__ void load_planes_frag(const uint8_t* phi, const uint8_t* plo, Frag& H) {
+// NS = 1: only the primal stream is fetched (ReLU gates need nothing else: relu'' = 0), the tangent entries of H are
+// left untouched - a quarter of the record's lines.
+template <int NS>
+__device__ __forceinline__ void load_planes_frag_n(const uint8_t* phi, const uint8_t* plo, Frag& H) {
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
+  for (int s = 0; s < NS; ++s) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(phi + j * A_LBO + s * 128));
@@ -907,6 +968,10 @@ __device__ __forceinline__ void load_planes_frag(const uint8_t* phi, const uint8
       H.f[s][2 * j + 1] = fa.y + fb.y;
     }
   }
+}
+__device__ __forceinline__ void load_planes_frag(const uint8_t* phi, const uint8_t* plo, Frag& H, int n_streams = 4) {
+  if (n_streams == 1) load_planes_frag_n<1>(phi, plo, H);
+  else load_planes_frag_n<4>(phi, plo, H);
 }
 
 // activation backward on a fragment (see bwd_gate_plain for the formulas); everything is thread-local
@@ -1050,6 +1115,9 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
       const int n_chunks = L.n_chunks;
       const bool side_dot = L.side_dot != 0;
       bool prev_waited = false;
+      if constexpr (BWD) {
+        if (!ES_FLAG(io, 8)) prefetch_next_gates(prog, io, gate_tile, l, tile + tw.step, tw.n_tiles, frag_off, true);
+      }
 
       if (!BWD && L.pre_op == PRE_DEFORM_TAIL) {
         // deform output layer (3 x 256, fp32 FFMA) -> x_c = x + delta ; tangent streams give dDelta/dx_{s-1}
@@ -1079,6 +1147,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
 
       for (int ck = 0; ck < n_chunks; ++ck, ++c.ac) {
         const uint32_t slot = claim_slot<DUMP>(c, ck);
+        if constexpr (DUMP) TRACE_EPI(6000 + l * 16 + ck);  // EPI: ring slot free
         const uint32_t slot_sa = c.sm + SM_A_OFF + slot * SLOT_BYTES;
         const int src = L.src[ck];
         const int blk = L.arg[ck];
@@ -1131,9 +1200,10 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
             }
             emit_frag(F, slot_sa + frag_off);
           } else {
-            Frag HG;  // gating activations first: their global-memory latency overlaps the accumulator wait
+            Frag HG;  // gating activations first: their latency (L2, see prefetch_next_gates) overlaps the accumulator wait
             const size_t go = static_cast<size_t>(L.gate_base + blk) * CHUNK_PLANE_BYTES + frag_off;
-            load_planes_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, HG);
+            load_planes_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, HG,
+                             L.bwd_act == ACT_RELU ? 1 : 4);
             if (src == SRC_BWD_PREV) {
               if (!prev_waited) {
                 wait_d_full(c, c.g - 1);
@@ -1210,7 +1280,8 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
       for (int blk = 0; blk < 4; ++blk, ++c.ac) {
         Frag F, HG;
         const size_t go = static_cast<size_t>(prog.post_gate_base + blk) * CHUNK_PLANE_BYTES + frag_off;
-        load_planes_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, HG);
+        load_planes_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, HG,
+                         prog.post_bwd_act == ACT_RELU ? 1 : 4);
         if (!waited) {
           wait_d_full(c, c.g - 1);
           waited = true;
@@ -1504,9 +1575,10 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       uint32_t slot = 0, a_par = 0;
       auto handle = [&](long long tile, int idx_hi, int idx_lo) {
         mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 500);
+        if (ES_FLAG(io, 32) && tile < tw.n_tiles) tile = blockIdx.x;  // ablation: records stay L2 resident (148 tiles)
         const uint32_t slot_sa = sm + SM_A_OFF + slot * SLOT_BYTES;
         bool any = false;
-        if (tile < tw.n_tiles) {  // (a pair's ghost tile keeps nothing)
+        if (tile < tw.n_tiles && !ES_FLAG(io, 16)) {  // (a pair's ghost tile keeps nothing)
           if (idx_hi != NO_DUMP && io.dump_hi) {
             tma_bulk_s2g(io.dump_hi + (static_cast<size_t>(tile) * prog.n_dump + idx_hi) * CHUNK_PLANE_BYTES, slot_sa,
                          CHUNK_PLANE_BYTES);

@@ -236,6 +236,8 @@ class EndoSurfRenderer(nn.Module):
                 raise _lib.EsError(f"es_create failed: {_lib.ES_E.get(rc, rc)}")
             self._ctx = ctx
             self.set_pair_mode(PAIR_MODE_DEFAULT)
+            if os.environ.get("ES_DEBUG_FLAGS"):  # ablation experiments; only -DES_ABLATE builds of the library look at it
+                lib.es_debug_set(ctx, 0, int(os.environ["ES_DEBUG_FLAGS"]))
         return self._ctx
 
     def set_pair_mode(self, on: bool):
