@@ -17,7 +17,7 @@ from conftest import load_cfg
 pytestmark = pytest.mark.gpu
 
 
-def _trainer(tmp_path, ray_batch=256, ns=16, ni=16, reference_renderer=False):
+def _trainer(tmp_path, ray_batch=256, ns=16, ni=16, reference_renderer=False, precision_terms=3, n_iter=100):
     tmp_path.mkdir(parents=True, exist_ok=True)
     from oracle import ref_shims
     if not ref_shims.available():
@@ -27,6 +27,9 @@ def _trainer(tmp_path, ray_batch=256, ns=16, ni=16, reference_renderer=False):
     te = importlib.import_module("src.trainer.trainer_endosurf")
     from endosurf_b200.harness import patch_reference_trainer
     patch_reference_trainer(te, tb, n_frames=8, hw=(96, 96))
+    if precision_terms != 3:  # the single-pass fp16 mode of this renderer (constructor keyword the reference lacks)
+        ours_cls = te.EndoSurfRenderer
+        te.EndoSurfRenderer = lambda *a, **k: ours_cls(*a, precision_terms=precision_terms, **k)
     if reference_renderer:  # the reference's own renderer (stock PyTorch on the GPU); only the dataset is the stand-in
         te.EndoSurfRenderer = importlib.import_module("src.renderer.endosurf").EndoSurfRenderer
     base = load_cfg()
@@ -34,7 +37,7 @@ def _trainer(tmp_path, ray_batch=256, ns=16, ni=16, reference_renderer=False):
         "exp": {"project_name": "endosurf", "exp_name": "b200_test", "exp_dir": str(tmp_path / "logs")},
         "data": {"info_dir": "synthetic", "normalize_time": True},
         "render": dict(copy.deepcopy(base["render"]), n_samples=ns, n_importance=ni),
-        "train": {"n_iter": 100, "ray_batch": ray_batch, "mask_guided_ray_sampling": True, "color_loss_weight": 1.0,
+        "train": {"n_iter": n_iter, "ray_batch": ray_batch, "mask_guided_ray_sampling": True, "color_loss_weight": 1.0,
                   "depth_loss_weight": 1.0, "sdf_loss_weight": 1.0, "angle_loss_weight": 0.1,
                   "eikonal_loss_weight": 0.1, "surf_neig_loss_weight": 0.1, "surf_neig_rad": 0.1, "resume": False,
                   "optim": {"lr": 5e-4, "lr_alpha": 0.05, "warm_up_end": 50}, "eval": {"ray_chunk": 2048}},
@@ -138,3 +141,72 @@ def test_host_syncs_per_train_step(tmp_path):
     print(f"host synchronisations in one reference train_step: {len(syncs)} (inside endosurf_b200: {n_renderer})")
     assert n_renderer <= 1, [str(x.filename) + ":" + str(x.lineno) for x in syncs if "endosurf_b200" in (x.filename or "")]
     assert len(syncs) <= 20
+
+
+def test_loss_curve_parity_200_steps(tmp_path):
+    """BASELINE configs[2] ("full EndoSurf training loop ... 1 GPU"): 200 optimisation steps of the UNMODIFIED reference
+    trainer, driven three times from the same initial state and the same per-step RNG seeds (frame, rays, jitter):
+    with the reference's own renderer (stock PyTorch fp32 on the GPU), with this renderer in the fp32-parity mode
+    and in the single-pass fp16 mode (precision_terms=1).  Training amplifies rounding differences (ReLU kinks,
+    re-sampling), so the curves are compared as 25-step window means; the band is stated at the assertions."""
+    n_steps, win = 200, 25
+    terms = ["train/loss_color", "train/loss_depth", "train/loss_sdf", "train/loss_eikonal", "train/loss_total"]
+
+    def run(kind):
+        tr, _ = _trainer(tmp_path / kind, reference_renderer=(kind == "ref"),
+                         precision_terms=1 if kind == "fp16x1" else 3, n_iter=n_steps)
+        return tr
+
+    curves = {}
+    init = None
+    for kind in ("ref", "fp16x3", "fp16x1"):
+        tr = run(kind)
+        if init is None:
+            init = copy.deepcopy(tr.renderer.save_checkpoint())  # (state dicts alias the live parameters)
+        else:
+            tr.renderer.load_checkpoint(init)
+        tr.writer = _Recorder()
+        tr.renderer.train()
+        tr.dset.list_train = tr.dset.list_train[:2]
+        rec = {k: [] for k in terms}
+        for it in range(1, n_steps + 1):
+            torch.manual_seed(1000 + it)
+            np.random.seed(1000 + it)
+            tr.train_step(global_step=it)
+            tr.update_learning_rate(it)
+            for k in terms:
+                rec[k].append(tr.writer.scalars[k])
+        if kind != "ref":
+            tr.renderer.sync_check()
+        curves[kind] = {k: np.asarray(v) for k, v in rec.items()}
+    ref = curves["ref"]
+    report = {}
+    for kind in ("fp16x3", "fp16x1"):
+        for k in terms:
+            a = ref[k].reshape(-1, win).mean(1)
+            b = curves[kind][k].reshape(-1, win).mean(1)
+            report[(kind, k)] = float(np.max(np.abs(a - b) / np.maximum(np.abs(a), 1e-3)))
+    print("loss-curve parity, worst relative deviation of a 25-step window mean from the reference's:",
+          {f"{kk[0]}:{kk[1].split('/')[-1]}": round(v, 4) for kk, v in report.items()})
+    print("total loss, first 12 steps ref / fp16x3 / fp16x1:",
+          [np.round(curves[c]["train/loss_total"][:12], 4).tolist() for c in ("ref", "fp16x3", "fp16x1")])
+    print("total-loss window means ref / fp16x3 / fp16x1:",
+          [np.round(curves[c]["train/loss_total"].reshape(-1, win).mean(1), 4).tolist() for c in ("ref", "fp16x3", "fp16x1")])
+    for c in curves:
+        t = curves[c]["train/loss_total"]
+        assert np.all(np.isfinite(t)), c
+        assert t[-win:].mean() < 0.8 * t[:win].mean(), (c, t[:win].mean(), t[-win:].mean())
+    # Stated band (measured on B200: total-loss window means 1.197/0.658/0.309/0.134/0.095/0.062/0.047/0.038 against the
+    # reference's 1.199/0.647/0.309/0.145/0.094/0.079/0.052/0.040; identical to 0.3 % over the first 12 steps): the total
+    # loss's 25-step window means within 5 % of the reference curve over the first 75 steps and within 30 % everywhere
+    # (late in the run the loss is small and the trajectories have decorrelated: different neighbour draws in
+    # surface_neighbour_error, ReLU kinks, re-sampling); every single loss term's window means within 60 %.
+    for kind in ("fp16x3", "fp16x1"):
+        a = ref["train/loss_total"].reshape(-1, win).mean(1)
+        b = curves[kind]["train/loss_total"].reshape(-1, win).mean(1)
+        rel = np.abs(a - b) / a
+        assert np.all(rel[:3] <= 0.05) and np.all(rel <= 0.30), (kind, rel.tolist())
+        first = np.abs(ref["train/loss_total"][:12] - curves[kind]["train/loss_total"][:12]) / ref["train/loss_total"][:12]
+        assert np.all(first <= 0.01), (kind, first.tolist())
+    for (kind, k), v in report.items():
+        assert v <= 0.60, (kind, k, v)
