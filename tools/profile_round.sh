@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
     $B --mode forward --steps 2 --warmup 3 >> $out/${tag}_ncu_launch.log 2>&1
 # full capture of the tensor-core kernels of ONE training step (5 sampling chains, geometry, colour, 3 reverse chains,
 # 3 input-adjoint launches, weight gradients = 15 launches; the first 3 steps are warm-up) and of the forward chains
-ncu --set full --clock-control none --import-source on -k regex:'mlp_chain_kernel|wgrad_kernel' -s 45 -c 15 \
+ncu --set full --clock-control none --import-source on -k regex:'mlp_chain_kernel|wgrad_kernel' -s 48 -c 16 \
     -o /tmp/${tag}_train -f $B --steps 1 --warmup 3 > $out/${tag}_ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mlp_chain_kernel -s 21 -c 7 -o /tmp/${tag}_forward -f \
     $B --mode forward --steps 1 --warmup 3 >> $out/${tag}_ncu_full.log 2>&1
