@@ -1124,6 +1124,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
         // training: the output layer's input leaves as 4 dump-only chunks (this layer has no SRC_PREV chunk of its own)
         float o[12];
         tail_frag<3>(c, c.g - 1, act_prev, bias_prev, prog.deform_out_w, STASH, frag_off, o);
+        TRACE_EPI(8000 + l);  // EPI: output-layer tail done
         if constexpr (STASH) c.ac += 4;
 #pragma unroll
         for (int i = 0; i < 3; ++i) xc[i] += o[i] + __ldg(prog.deform_out_b + i);
@@ -1143,6 +1144,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
           }
         }
         prev_waited = true;  // (already consumed and released)
+        TRACE_EPI(9000 + l);  // EPI: tail outputs stored
       }
 
       for (int ck = 0; ck < n_chunks; ++ck, ++c.ac) {
@@ -1309,6 +1311,7 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
         }
       }
       release_d(c, c.g - 1);
+      TRACE_EPI(8000 + 99);  // EPI: feature rows stored
     } else if (BWD && prog.post_op == POST_INADJ_SDF) {
       // adjoint of the enc6(x_c) rows (accumulator columns 0..63 in the kernel's chunk order; primal + tangent rows)
       // pushed back to x_c.  Row form: this thread is TMEM lane 32Q + lane = stream lane>>3 of point lane&7.

@@ -190,6 +190,14 @@ def test_render_rays_end_to_end(cfg, ckpt, tag, use_deform):
     assert_close("z_vals", o["z_vals"], g["z_vals"], TOL, kink_tol=KINK, q=0.98)
     for k in ["color_map", "depth_map"]:
         assert_close(k, o[k], g[k], TOL, kink_tol=KINK, q=0.98)
+    # the flip rate itself, reported and bounded: share of samples / rays beyond 1e-4 (of the abs-max)
+    rates = {}
+    for k in ["z_vals", "color_map", "depth_map"]:
+        a, b = o[k].double().cpu().flatten(), torch.from_numpy(g[k]).double().flatten()
+        rates[k] = ((a - b).abs() / b.abs().max() > TOL).double().mean().item()
+    print(f"[resampling flips] {tag}: beyond 1e-4: z_vals {100 * rates['z_vals']:.3f} % of samples, colour "
+          f"{100 * rates['color_map']:.3f} % / depth {100 * rates['depth_map']:.3f} % of ray entries")
+    assert max(rates.values()) <= 0.02, rates
     for k in ["s_val", "gradient_o_error"]:
         assert_close(k, o[k], g[k], TOL)
     assert_close("weight_max", o["weight_max"], g["weight_max"], 1e-3)

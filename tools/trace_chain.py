@@ -43,10 +43,10 @@ ev = np.concatenate([buf[2:2 + 2 * n0].reshape(-1, 2), buf[2 + 8000:2 + 8000 + 2
 cnt = n0 + n1
 ev = ev[np.argsort(ev[:, 0])]; t0 = ev[0, 0]
 names = {1: "MMA layer start", 2: "MMA chunk ready", 3: "MMA layer issued", 4: "EPI acc ready", 5: "EPI chunk written",
-         6: "EPI  slot free", 7: "EPI  values ready", 8: "EPI  stores issued", 9: "EPI  fence done"}
+         6: "EPI  slot free", 7: "EPI  values ready", 8: "EPI  tail done", 9: "EPI  tail stored"}
 print("events", cnt)
 last = {}
 for clk, code in ev[:int(os.environ.get('ES_TRACE_EVENTS', '400'))]:
     k = code // 1000; rest = code % 1000
-    what = f"L{rest}" if k in (1, 3, 4) else f"L{rest // 16} c{rest % 16}"
+    what = f"L{rest}" if k in (1, 3, 4, 8, 9) else f"L{rest // 16} c{rest % 16}"
     print(f"{clk - t0:9d}  {names[k]:18s} {what}")
