@@ -185,7 +185,9 @@ def test_loss_curve_parity_200_steps(tmp_path):
         for k in terms:
             a = ref[k].reshape(-1, win).mean(1)
             b = curves[kind][k].reshape(-1, win).mean(1)
-            report[(kind, k)] = float(np.max(np.abs(a - b) / np.maximum(np.abs(a), 1e-3)))
+            # relative to the reference window, floored at a tenth of the term's initial level (late in the run single
+            # terms are ~1e-3 and the reference itself varies by tens of percent from run to run: atomics)
+            report[(kind, k)] = float(np.max(np.abs(a - b) / np.maximum(np.abs(a), 0.1 * np.abs(a[0]))))
     print("loss-curve parity, worst relative deviation of a 25-step window mean from the reference's:",
           {f"{kk[0]}:{kk[1].split('/')[-1]}": round(v, 4) for kk, v in report.items()})
     print("total loss, first 12 steps ref / fp16x3 / fp16x1:",
