@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import weakref
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -146,6 +147,46 @@ class EndoSurfNet(nn.Module):
         self.color_network.load_state_dict(ckpt["color_network"])
         self.deviation_network.load_state_dict(ckpt["deviation_network"])
 
+    # ---- the reference's query methods (endosurf.py:570-689).  The parameters live here, the kernels in the renderer
+    # that owns this module; every query is one fused chain launch (differentiable when grad is enabled).
+    def _owner(self):
+        r = self.__dict__.get("_renderer_ref")
+        r = r() if r is not None else None
+        if r is None:
+            raise RuntimeError("EndoSurfNet queries need the EndoSurfRenderer that owns this module")
+        return r
+
+    def _fields(self, x, d, t):
+        r = self._owner()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            x = x.reshape(-1, 3)
+            if d is None:  # geometry-only query: the colour chain still runs on a dummy view direction
+                d = torch.zeros_like(x)
+                d[:, 2] = 1.0
+            return r.point_field(x, d.reshape(-1, 3), t.reshape(-1, 1))
+        o = r.point_forward(x, d, t)
+        return o["sdf"], o["g_c"], o["jac"], o.get("rgb")
+
+    def get_sdf_from_observed_space(self, x, t):
+        """endosurf.py:570-579 -> [n,1]"""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._fields(x, None, t)[0]
+        return self._owner().sdf_from_observed_space(x, t)
+
+    def get_sdf_grad_from_observed_space(self, x, t):
+        """endosurf.py:581-601 -> [n,3]: d sdf / d x = J^T g_c"""
+        _, g_c, jac, _ = self._fields(x, None, t)
+        return (jac * g_c[:, :, None]).sum(1)
+
+    def get_deform_grad_from_observed_space(self, x, t):
+        """endosurf.py:621-658 -> [n,3,3]: J[i,j] = d x_c_i / d x_j"""
+        return self._fields(x, None, t)[2]
+
+    def forward(self, inputs):
+        """endosurf.py:660-689: inputs [n,7] = (x, d, t) -> cat[sdf, rgb] [n,4]"""
+        sdf, _, _, rgb = self._fields(inputs[:, :3], inputs[:, 3:6], inputs[:, 6:7])
+        return torch.cat([sdf, rgb], dim=-1)
+
 
 def _net_config_struct(net_cfg: dict, precision_terms: int) -> _lib.EsNetConfig:
     s, c = net_cfg["sdf_network"], net_cfg["color_network"]
@@ -190,6 +231,7 @@ class EndoSurfRenderer(nn.Module):
         if self.dtype != torch.float32:
             raise NotImplementedError("endosurf_b200 computes in fp32 storage (fp16 hi/lo split tensor-core products)")
         self.model = EndoSurfNet(net_cfg).to(device)
+        self.model.__dict__["_renderer_ref"] = weakref.ref(self)  # (not a sub-module: the queries run in this object)
         self.anneal_end = render_cfg["anneal_end"]
         self.n_samples = render_cfg["n_samples"]
         self.perturb = render_cfg["perturb"]
@@ -332,7 +374,8 @@ class EndoSurfRenderer(nn.Module):
                    "es_render_rays(sampling)")
         return z
 
-    def _render_rays_train(self, rays, iter_step, perturb_overwrite, z_vals_override=None, return_extras=False):
+    def _render_rays_train(self, rays, iter_step, perturb_overwrite, z_vals_override=None, return_extras=False,
+                           cos_ratio=None):
         """render_rays with autograd (endosurf.py:60-213): sampling runs without grad exactly as in the reference
         (:86); everything after it - points, the three MLPs with normals and Jacobian, compositing - is one fused
         library forward and one library backward (training.RenderFn)."""
@@ -342,7 +385,7 @@ class EndoSurfRenderer(nn.Module):
         with torch.no_grad():
             z = z_vals_override.detach().contiguous().float() if z_vals_override is not None else \
                 self._sample_z(rays, iter_step, perturb_overwrite)
-        cos_ratio = self.get_cos_anneal_ratio(iter_step)
+        cos_ratio = self.get_cos_anneal_ratio(iter_step) if cos_ratio is None else float(cos_ratio)
         params = param_list(self)
         variance = self.model.deviation_network.variance
         names = ["color_map", "depth_map", "gradients_o", "gradient_o_error", "weights", "cdf", "sdf",
@@ -605,12 +648,50 @@ class EndoSurfRenderer(nn.Module):
                                          float(inv_s), _ptr(out), self._stream()), "es_up_sample")
         return out
 
+    def cat_z_vals(self, rays_o, rays_d, time, z_vals, new_z_vals, sdf, last=False):
+        """endosurf.py:268-287: merge new samples into the sorted z list; unless `last`, query the SDF at the new
+        samples (fused deform + SDF chain) and permute it alongside.  (render_rays itself runs this step as
+        merge_z_kernel inside es_render_rays; this method keeps the reference's name and signature for callers.)"""
+        R, n = z_vals.shape
+        z_all, index = torch.sort(torch.cat([z_vals, new_z_vals], dim=-1), dim=-1)
+        if not last:
+            rays_d_z = rays_d / (rays_d[..., 2:] + 1e-6)
+            pts = rays_o[:, None, :] + rays_d_z[:, None, :] * new_z_vals[..., :, None]
+            t = time.reshape(R, 1, 1).expand(R, new_z_vals.shape[1], 1)
+            new_sdf = self.sdf_from_observed_space(pts.reshape(-1, 3), t.reshape(-1, 1)).reshape(R, -1)
+            sdf = torch.gather(torch.cat([sdf.reshape(R, n), new_sdf], dim=-1), 1, index)
+        return z_all, sdf
+
+    def render_core(self, rays_o, rays_d, time, z_vals, sample_dist, cos_anneal_ratio=0.0, eval=False):
+        """endosurf.py:134-213 under the reference's name and signature: mid-points, the three networks with normals
+        and Jacobian, NeuS compositing on the given z_vals.  sample_dist must be 2 / n for an integer n <= the number
+        of samples (the reference always passes 2 / n_samples, endosurf.py:73)."""
+        R, M = z_vals.shape
+        ns = int(round(2.0 / float(sample_dist)))
+        if ns < 2 or abs(2.0 / ns - float(sample_dist)) > 1e-6 * float(sample_dist) or M < ns:
+            raise NotImplementedError("render_core: sample_dist must equal 2 / n with 2 <= n <= z_vals.shape[1]")
+        dev = z_vals.device
+        rays = torch.cat([rays_o.reshape(R, 3), rays_d.reshape(R, 3), torch.zeros(R, 2, device=dev),
+                          time.reshape(R, 1)], dim=-1).float()
+        saved = (self.n_samples, self.n_importance, self.important_begin_iter)
+        try:
+            self.n_samples, self.n_importance, self.important_begin_iter = ns, M - ns, 0
+            o = self.render_rays(rays, iter_step=0, perturb_overwrite=False, z_vals_override=z_vals,
+                                 cos_anneal_ratio=float(cos_anneal_ratio))
+        finally:
+            self.n_samples, self.n_importance, self.important_begin_iter = saved
+        return {"color_map": o["color_map"], "depth_map": o["depth_map"], "gradients_o": o["gradients_o"],
+                "gradient_o_error": o["gradient_o_error"], "cdf": o["cdf"], "weights": o["weights"],
+                "s_val": o["s_val"].expand(R, M).reshape(-1, 1)}
+
     # ------------------------------------------------------------------ the hot path
     def render_rays(self, rays, iter_step=0, perturb_overwrite=None, eval=False, z_vals_override=None,
-                    return_extras=False, **kwargs):
-        """EndoSurfRenderer.render_rays (endosurf.py:60-132): rays [R,9] -> the reference's 8-key dict."""
+                    return_extras=False, cos_anneal_ratio=None, **kwargs):
+        """EndoSurfRenderer.render_rays (endosurf.py:60-132): rays [R,9] -> the reference's 8-key dict.
+        cos_anneal_ratio: overrides get_cos_anneal_ratio(iter_step) (render_core passes the caller's value)."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
-            return self._render_rays_train(rays, iter_step, perturb_overwrite, z_vals_override, return_extras)
+            return self._render_rays_train(rays, iter_step, perturb_overwrite, z_vals_override, return_extras,
+                                           cos_anneal_ratio)
         self._sync_weights()
         lib, ctx = _lib.load(), self._context()
         rays = rays.detach().contiguous().float()
@@ -647,7 +728,8 @@ class EndoSurfRenderer(nn.Module):
             raise ValueError(f"z_vals_override must be [{R},{M}] for this render config, got {tuple(zo.shape)}")
         prm = _lib.EsRenderParams(
             n_samples=ns, n_importance=ni, up_sample_steps=steps, do_upsample=int(do_up),
-            cos_anneal_ratio=float(self.get_cos_anneal_ratio(iter_step)),
+            cos_anneal_ratio=float(self.get_cos_anneal_ratio(iter_step) if cos_anneal_ratio is None
+                                   else cos_anneal_ratio),
             variance=self.model.deviation_network.variance.data_ptr(), t_vals=t_vals.data_ptr(),
             u_vals=u_vals.data_ptr() if u_vals is not None else None,
             t_rand=t_rand.data_ptr() if t_rand is not None else None,
