@@ -296,6 +296,25 @@ __device__ __forceinline__ void load_planes(const uint8_t* phi, const uint8_t* p
   }
 }
 
+// raw hi-plane words of load_planes (the plo == nullptr case), fetched before the accumulator wait and unpacked at the
+// use: 8 live registers instead of 16 floats
+__device__ __forceinline__ void load_gate_raw(const uint8_t* phi, uint4 (&g)[PCOLS / 8]) {
+#pragma unroll
+  for (int k = 0; k < PCOLS / 8; ++k) g[k] = __ldg(reinterpret_cast<const uint4*>(phi + k * A_LBO));
+}
+__device__ __forceinline__ void unpack_gate_raw(const uint4 (&g)[PCOLS / 8], float (&h)[PCOLS]) {
+#pragma unroll
+  for (int k = 0; k < PCOLS / 8; ++k) {
+    const uint32_t w[4] = {g[k].x, g[k].y, g[k].z, g[k].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      h[8 * k + 2 * j] = f.x;
+      h[8 * k + 2 * j + 1] = f.y;
+    }
+  }
+}
+
 // SRC_PLANE: copy this row's 16-byte units (k-groups 2 part, 2 part + 1; hi and lo halves) of a dumped chunk into the
 // ring slot.  off = 2 part A_LBO + 16 row (the same offset in the chunk and in the slot half).
 __device__ __forceinline__ void copy_plane_row(uint32_t slot_sa, const uint8_t* chi, const uint8_t* clo, uint32_t off) {
@@ -633,6 +652,15 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
       for (int i = 0; i < 3; ++i) xc[i] = __ldg(io.x + pt * 3 + i);
     }
     float sdf_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (!BWD && CHAIN == CHAIN_COLOR) {
+      // the geometry feature rows (1 KiB per point, read on demand by the SRC_FEAT chunks of layer 0 and of the skip
+      // layer) of the CTA's NEXT tile go to L2 now: a whole tile of MMAs later the loads no longer wait for HBM
+      const long long pn = (tile + tw.step) * TILE_ROWS + c.row;
+      if (pn < io.n_points && io.feat) {
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) prefetch_l2(io.feat + pn * HID + 64 * blk + PCOLS * c.part);
+      }
+    }
     const uint8_t* gate_tile =
         BWD ? io.gate_hi + static_cast<size_t>(tile_r) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
     const uint8_t* gate_tile_lo =
@@ -671,6 +699,11 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
         const int col0 = 64 * L.arg[ck] + PCOLS * c.part;
         if (BWD && (src == SRC_BWD_PREV || src == SRC_BWD_OUTER3)) {
           float v[PCOLS];
+          // gating activations first (hi-only records: raw words), so that their L2 latency overlaps the accumulator
+          // wait and the TMEM load
+          const size_t go = static_cast<size_t>(L.gate_base + L.arg[ck]) * CHUNK_PLANE_BYTES + row_off;
+          uint4 graw[PCOLS / 8];
+          if (!gate_tile_lo) load_gate_raw(gate_tile + go, graw);
           if (src == SRC_BWD_PREV) {
             if (!prev_waited) {
               wait_d_full(c, c.g - 1);
@@ -688,10 +721,10 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
               v[i] = adj[0] * __ldg(prog.outer3_w + col0 + i) + adj[1] * __ldg(prog.outer3_w + HID + col0 + i) +
                      adj[2] * __ldg(prog.outer3_w + 2 * HID + col0 + i);
           }
-          {  // (row form: 16 more live registers for an early fetch spill at the 96-register budget - measured slower)
+          {
             float hg[PCOLS];
-            const size_t go = static_cast<size_t>(L.gate_base + L.arg[ck]) * CHUNK_PLANE_BYTES + row_off;
-            load_planes(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, hg);
+            if (gate_tile_lo) load_planes(gate_tile + go, gate_tile_lo + go, hg);
+            else unpack_gate_raw(graw, hg);
             bwd_gate_plain(hg, L.bwd_act, v);
           }
           emit_row(row_sa, v);
@@ -774,9 +807,12 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
 #pragma unroll 1
       for (int blk = 0; blk < 4; ++blk, ++c.ac) {
         float v[PCOLS], hg[PCOLS];
-        load_raw(c, (c.g - 1) & 1, blk, v);
         const size_t go = static_cast<size_t>(prog.post_gate_base + blk) * CHUNK_PLANE_BYTES + row_off;
-        load_planes(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, hg);
+        uint4 graw[PCOLS / 8];
+        if (!gate_tile_lo) load_gate_raw(gate_tile + go, graw);  // before the TMEM load: latencies overlap
+        load_raw(c, (c.g - 1) & 1, blk, v);
+        if (gate_tile_lo) load_planes(gate_tile + go, gate_tile_lo + go, hg);
+        else unpack_gate_raw(graw, hg);
         bwd_gate_plain(hg, prog.post_bwd_act, v);
         const uint32_t slot = claim_slot<true>(c, blk);
         emit_row(c.sm + SM_A_OFF + slot * SLOT_BYTES + row_off, v);
@@ -1102,6 +1138,15 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
       for (int i = 0; i < 3; ++i) xc[i] = __ldg(io.x + pt * 3 + i);
     }
     float sdf_acc[4][1] = {{0.f}, {0.f}, {0.f}, {0.f}};
+    if constexpr (BWD) {
+      // reverse SDF chain: the adjoint of the geometry feature (fp32 [P,256], read on demand by the SRC_ADJ_FEAT chunks
+      // of layer 0) of the CTA's next tile goes to L2 now
+      const long long pn = (tile + tw.step) * TILE_PTS_T + 8 * c.quad + p;
+      if (io.adj_feat && pn < io.n_points) {
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) prefetch_l2(io.adj_feat + pn * HID + 64 * blk + colq);
+      }
+    }
     const uint8_t* gate_tile =
         BWD ? io.gate_hi + static_cast<size_t>(tile_r) * prog.n_gate * CHUNK_PLANE_BYTES : nullptr;
     const uint8_t* gate_tile_lo =
