@@ -315,7 +315,7 @@ def run_ours(args):
         return run_latency(args, r, dev, world, rank)
     params = [p for v in r.get_train_params().values() for p in v]
     opt = torch.optim.Adam(params, lr=5e-4) if train else None
-    bucket = dp.FlatGradBucket(params) if train else None
+    bucket = dp.FlatGradBucket(params).bind(r) if train else None
     R, K, W = args.rays, args.steps, args.warmup
     n_batches = min(K + W, 16)
     frames = [(rank * 17 + i) % 60 for i in range(n_batches)]

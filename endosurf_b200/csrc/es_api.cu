@@ -1248,6 +1248,8 @@ struct BwdScratch {
   float* bias_partial = nullptr;
   float* small_part = nullptr;
   float* gw_eff[3][16] = {};
+  uint8_t* gw_first = nullptr;
+  size_t gw_bytes = 0;
 };
 void carve_backward(const es_ctx* ctx, int64_t n, int n_items, Carver& c, BwdScratch& s) {
   const StashLayout sl = stash_layout(ctx, n);
@@ -1264,9 +1266,13 @@ void carve_backward(const es_ctx* ctx, int64_t n, int n_items, Carver& c, BwdScr
   s.partial = c.take<float>(static_cast<size_t>(n_items) * TILE_ROWS * HID);
   s.bias_partial = c.take<float>(static_cast<size_t>(n_items) * TILE_ROWS);
   s.small_part = c.take<float>(static_cast<size_t>(3) * 2 * ctx->n_sms * (4 * HID + 4));
+  s.gw_first = nullptr;
   for (int net = 0; net < 3; ++net)
-    for (int l = 0; l < ctx->cfg.n_layers; ++l)
+    for (int l = 0; l < ctx->cfg.n_layers; ++l) {
       s.gw_eff[net][l] = c.take<float>(static_cast<size_t>(ctx->plan[net].out_dims[l]) * ctx->plan[net].in_dims[l]);
+      if (!s.gw_first) s.gw_first = reinterpret_cast<uint8_t*>(s.gw_eff[net][l]);
+    }
+  s.gw_bytes = c.base ? static_cast<size_t>(c.base + c.off - s.gw_first) : 0;  // contiguous: cleared by one memset
   s.bytes = c.off + 256;
 }
 
@@ -1281,11 +1287,7 @@ int backward_core(es_ctx* ctx, const BwdIn& a, const BwdScratch& s, es_ctx::Wgra
   const bool full = ctx->full_planes != 0;
   es_ctx::Timed t;
   CU(cudaMemsetAsync(ctx->amax_dev, 0, 4 * sizeof(unsigned int), stream));
-  for (int net = 0; net < 3; ++net)
-    for (int l = 0; l < L; ++l)
-      CU(cudaMemsetAsync(s.gw_eff[net][l], 0,
-                         static_cast<size_t>(ctx->plan[net].out_dims[l]) * ctx->plan[net].in_dims[l] * sizeof(float),
-                         stream));
+  CU(cudaMemsetAsync(s.gw_first, 0, s.gw_bytes, stream));  // every effective-weight gradient (carved contiguously)
   auto rev_chain = [&](int net, const float* adj, const float* adj_feat) -> int {
     ChainIO io{};
     io.n_points = n;

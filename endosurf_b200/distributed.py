@@ -53,6 +53,31 @@ class FlatGradBucket:
         self.flat.zero_()
         self.attach()
 
+    def bind(self, renderer):
+        """Let ``renderer``'s backward calls add their gradients straight into this buffer (one launch per call) instead
+        of returning 82 tensors for autograd to accumulate one by one.  Only for steps that call ``loss.backward()``
+        (as ``dp_backward`` does) - ``torch.autograd.grad`` would not see these gradients."""
+        renderer._grad_sink = self
+        return self
+
+    def accumulate(self, params, flat_grads: torch.Tensor, extra) -> bool:
+        """flat_grads: the gradients of ``params`` (in that order) as one flat tensor; extra: [(parameter, gradient)].
+        Returns False (nothing done) unless the buffer is laid out in exactly this order and attached."""
+        n = len(params)
+        mine = self.params
+        if len(mine) < n or any(a is not b for a, b in zip(mine[:n], params)):
+            return False
+        if any(p.grad is None or p.grad.data_ptr() != v.data_ptr() for p, v in zip(mine, self.views)):
+            return False
+        index = {id(p): i for i, p in enumerate(mine)}
+        if any(id(p) not in index for p, _ in extra):
+            return False
+        with torch.no_grad():
+            self.flat[:flat_grads.numel()].add_(flat_grads)
+            for p, g in extra:
+                self.views[index[id(p)]].add_(g)
+        return True
+
     @property
     def extra(self) -> torch.Tensor:
         return self.flat[self.n_grad:]

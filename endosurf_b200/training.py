@@ -51,13 +51,21 @@ class _ParamTables:
         self.grads = []
         self.keep = []
         fields = {k: [None, None, None] for k in ("v", "g", "grad_v", "grad_g", "grad_b")}
+        # ONE zero-filled buffer for all gradients in parameter order (one fill launch; the bias gradients are
+        # accumulated by the kernels), handed out as views
+        self.flat = torch.zeros(sum(p.numel() for p in params), device=params[0].device, dtype=torch.float32)
+        off = 0
+        views = []
+        for p in params:
+            views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
         k = 0
         for net in net_ids(renderer):
             tabs = {n: (C.c_void_p * L)() for n in fields}
             for l in range(L):
                 b, g, v = params[k], params[k + 1], params[k + 2]
+                gb, gg, gv = views[k], views[k + 1], views[k + 2]
                 k += 3
-                gb, gg, gv = torch.zeros_like(b), torch.empty_like(g), torch.empty_like(v)
                 self.grads += [gb, gg, gv]
                 tabs["v"][l], tabs["g"][l] = v.data_ptr(), g.data_ptr()
                 tabs["grad_v"][l], tabs["grad_g"][l], tabs["grad_b"][l] = gv.data_ptr(), gg.data_ptr(), gb.data_ptr()
@@ -66,6 +74,17 @@ class _ParamTables:
                 self.keep.append(tabs[n])
         self.struct = _lib.EsTrainParams(**{n: (C.POINTER(C.c_void_p) * 3)(*[p if p is not None else C.POINTER(C.c_void_p)()
                                                                            for p in fields[n]]) for n in fields})
+
+
+def _deliver(renderer, params, tabs, extra):
+    """Hand the gradients of a backward call to autograd - or, when a gradient sink is bound to the renderer
+    (``distributed.FlatGradBucket.bind``: every ``p.grad`` is a view into one flat buffer laid out in exactly this
+    parameter order), add them there with ONE launch and return ``None`` for them, instead of the 80+ per-parameter
+    accumulation launches autograd would issue.  ``extra`` = [(parameter, gradient)] delivered the same way."""
+    sink = getattr(renderer, "_grad_sink", None)
+    if sink is not None and sink.accumulate(params, tabs.flat, extra):
+        return [None] * len(extra), [None] * len(params)
+    return [g for _, g in extra], list(tabs.grads)
 
 
 def _check_params(params):
@@ -151,7 +170,8 @@ class RenderFn(torch.autograd.Function):
                                           _ptr(var_grad), renderer._stream())
         _lib.check(ectx, rc, "es_render_train_backward")
         renderer._poll_device_error()
-        return (None, None, None, None, var_grad.reshape(variance.shape), *tabs.grads)
+        (vg,), grads = _deliver(renderer, ctx.params, tabs, [(variance, var_grad.reshape(variance.shape))])
+        return (None, None, None, None, vg, *grads)
 
 
 class PointFieldFn(torch.autograd.Function):
@@ -200,4 +220,5 @@ class PointFieldFn(torch.autograd.Function):
                                          C.byref(tabs.struct), renderer._stream())
         _lib.check(ectx, rc, "es_point_train_backward")
         renderer._poll_device_error()
-        return (None, None, None, None, *tabs.grads)
+        _, grads = _deliver(renderer, ctx.params, tabs, [])
+        return (None, None, None, None, *grads)

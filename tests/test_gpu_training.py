@@ -306,3 +306,36 @@ def test_data_parallel_shards_equal_the_union_batch(cfg, ckpt):
     r.sync_check()
     err = ((total - ref).norm() / ref.norm()).item()
     assert err < 2e-5, f"sum of shard gradients vs union-batch gradient: rel err {err:.3e}"
+
+
+def test_gradient_sink_equals_autograd_accumulation(cfg, ckpt):
+    """distributed.FlatGradBucket.bind: the backward adds its gradients into the flat bucket with one launch instead of
+    handing 82 tensors to autograd - the bucket must end up bit-identical to the unbound path, across two accumulated
+    backward calls (render_rays + a point-field loss, as the reference's train_step has)."""
+    from oracle import endosurf_oracle as orc
+    from endosurf_b200 import distributed as dp
+    r, rc, nc = _renderer(cfg, ckpt, 16, 16)
+    rays = orc.synthetic_rays(96, frame=5, seed=8).cuda()
+    with torch.no_grad():
+        z = r._sample_z(rays, 1000, False)
+    params = [p for v in r.get_train_params().values() for p in v]
+    bucket = dp.FlatGradBucket(params)
+    x = torch.rand(160, 3, device="cuda") - 0.5
+    d = torch.nn.functional.normalize(torch.randn(160, 3, device="cuda"), dim=-1)
+    t = torch.rand(160, 1, device="cuda")
+
+    def run(bound):
+        r._grad_sink = bucket if bound else None
+        bucket.zero()
+        o = r.render_rays(rays, iter_step=1000, z_vals_override=z)
+        sdf, g_c, jac, rgb = r.point_field(x, d, t)
+        loss = o["color_map"].sum() + o["depth_map"].sum() + o["gradient_o_error"] + sdf.abs().mean() + rgb.mean()
+        n0 = r.launch_count()
+        loss.backward()
+        r.sync_check()
+        return bucket.flat.clone()
+
+    a, b = run(False), run(True)
+    r._grad_sink = None
+    assert torch.equal(a, b), (a - b).abs().max().item()
+    assert a.abs().sum().item() > 0
