@@ -107,6 +107,7 @@ struct es_ctx {
   int debug_flags = 0;
   long long* trace_dev = nullptr;  // debug pipeline trace buffer (es_debug_trace)
   int trace_kind = -1;
+  int feat_records = 1;            // geometry feature travels to the colour chain as fp16 plane records (0: fp32 rows)
   struct Timed {
     int kind;
     long long points;
@@ -954,9 +955,18 @@ int es_sdf_grid(es_ctx* ctx, const float* bound_min3, const float* bound_max3, i
   return 0;
 }
 
+// bytes of the geometry-feature plane records of n points (colour tiles of 128 points, 4 chunks x (hi, lo) x 16 KiB)
+static size_t feat_rec_bytes(int64_t n) {
+  return static_cast<size_t>((n + TILE_ROWS - 1) / TILE_ROWS) * 4 * 2 * SLOT_HALF_BYTES;
+}
+
+// feat: the caller wants the fp32 feature rows (the colour chain then reads those).  Otherwise the feature goes from
+// the geometry chain to the colour chain as fp16 hi/lo plane records (ChainIO::out_feat_rec) in feat_rec, or, when
+// that is null too, in scratch carved here.
 static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64_t t_div, int64_t t_stride,
                               const float* dirs, int64_t dir_div, int64_t dir_stride, int64_t n, float* x_c, float* jac,
-                              float* sdf, float* g_c, float* feat, float* rgb, uint8_t* stash, void* stream_) {
+                              float* sdf, float* g_c, float* feat, float* rgb, uint8_t* stash, void* stream_,
+                              uint8_t* feat_rec = nullptr) {
   if (!ctx || n < 0 || t_div <= 0) return ES_E_BADARG;
   if (n == 0) return 0;
   if (!x) return ES_E_BADARG;
@@ -973,7 +983,7 @@ static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64
     if (!x_c) c.take<float>(n * 3);
     if (!jac && deform) c.take<float>(n * 9);
     if (!g_c) c.take<float>(n * 3);
-    if (!feat) c.take<float>(n * HID);
+    if (!feat && !feat_rec && want_color) c.take<uint8_t>(feat_rec_bytes(n));  // (also large enough for fp32 rows)
     need = c.off + 256;
   }
   if (int r = ensure_ws(ctx, need)) return r;
@@ -982,8 +992,15 @@ static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64
   if (!x_c) x_c = c.take<float>(n * 3);
   if (!jac && deform) jac = c.take<float>(n * 9);
   if (!g_c) g_c = c.take<float>(n * 3);
-  if (!feat) feat = c.take<float>(n * HID);
+  if (!feat && !feat_rec && want_color) feat_rec = c.take<uint8_t>(feat_rec_bytes(n));
+  if (feat) feat_rec = nullptr;
+  if (feat_rec && !ctx->feat_records) {  // A/B switch: the same scratch holds the fp32 rows instead
+    feat = reinterpret_cast<float*>(feat_rec);
+    feat_rec = nullptr;
+  }
   const StashLayout sl = stash_layout(ctx, n);
+  if (feat_rec && n % TILE_ROWS != 0)  // rows past n of the last colour tile: finite values for the MMAs and records
+    CU(cudaMemsetAsync(feat_rec + feat_rec_bytes(n) - 4 * 2 * SLOT_HALF_BYTES, 0, 4 * 2 * SLOT_HALF_BYTES, stream));
 
   ChainIO io{};
   io.n_points = n;
@@ -997,6 +1014,7 @@ static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64
   io.out_sdf = sdf;
   io.out_gc = g_c;
   io.out_feat = feat;
+  io.out_feat_rec = want_color ? feat_rec : nullptr;
   if (stash) {
     io.dump_hi = stash + sl.geom_hi;
     io.dump_lo = ctx->full_planes ? stash + sl.geom_lo : nullptr;
@@ -1021,6 +1039,7 @@ static int point_forward_impl(es_ctx* ctx, const float* x, const float* t, int64
     ic.dir_div = dir_div;
     ic.dir_stride = dir_stride;
     ic.feat = feat;
+    ic.feat_rec = feat_rec;
     ic.out_rgb = rgb;
     if (stash) {
       ic.dump_hi = stash + sl.color_hi;
@@ -1493,7 +1512,7 @@ int es_render_train_forward(es_ctx* ctx, const float* rays, int64_t n_rays, cons
   const int64_t n = n_rays * m;
   const float sample_dist = 2.0f / static_cast<float>(n_samples);
   // mid-points and per-ray partials live past the scratch point_forward_impl carves for itself (feat)
-  const size_t fwd_need = static_cast<size_t>(n) * HID * sizeof(float) + 1024;
+  const size_t fwd_need = feat_rec_bytes(n) + 1024;
   size_t off_pts, off_eik, need;
   {
     Carver c(nullptr);
@@ -1664,6 +1683,7 @@ int es_debug_set(es_ctx* ctx, int32_t key, int32_t value) {
     case 2: ctx->wgrad_sbo = value; return 0;
     case 3: ctx->scale_target = std::ldexp(1.f, value); return 0;  // adjoint scale target 2^value
     case 5: ctx->wgrad_pairs = value != 0; return 0;
+    case 7: ctx->feat_records = value != 0; return 0;  // A/B switch of the feature plane records
     case 6: ctx->trace_kind = value; return 0;    // ES_TRACE builds: only launches of this kind write the trace (-1: all)
     case 4:  // CTA pairs on/off; the packed weights change layout: the networks must be loaded again
       ctx->pair_mode = value != 0;
@@ -1726,7 +1746,7 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
     c.take<float>(PC * 3);      // g_c
     c.take<float>(PC);          // sdf
     c.take<float>(PC * 3);      // rgb
-    c.take<float>(PC * HID);    // feat
+    c.take<uint8_t>(feat_rec_bytes(PC));  // geometry-feature plane records
     c.take<float>(n_rays * 2);  // eikonal partials (all rays)
     need = c.off + 256;
   }
@@ -1745,7 +1765,7 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
   float* g_c = c.take<float>(PC * 3);
   float* sdf = c.take<float>(PC);
   float* rgb = c.take<float>(PC * 3);
-  float* feat = c.take<float>(PC * HID);
+  uint8_t* feat_rec = c.take<uint8_t>(feat_rec_bytes(PC));
   float* eik = c.take<float>(n_rays * 2);
 
   for (int64_t r0 = 0; r0 < n_rays; r0 += RC) {
@@ -1794,8 +1814,8 @@ int es_render_rays(es_ctx* ctx, const float* rays, int64_t n_rays, const es_rend
     ++ctx->launches;
     float* sdf_dst = out->sdf ? out->sdf + r0 * M : sdf;
     float* rgb_dst = out->sampled_color ? out->sampled_color + r0 * M * 3 : rgb;
-    if (int rr = es_point_forward(ctx, pts, tptr, n, 9, rays + r0 * 9 + 3, n, 9, R * n, x_c, deform ? jac : nullptr,
-                                  sdf_dst, g_c, feat, rgb_dst, stream_))
+    if (int rr = point_forward_impl(ctx, pts, tptr, n, 9, rays + r0 * 9 + 3, n, 9, R * n, x_c, deform ? jac : nullptr,
+                                    sdf_dst, g_c, nullptr, rgb_dst, nullptr, stream_, feat_rec))
       return rr;
     CompositeOut co;
     co.color_map = out->color_map + r0 * 3;

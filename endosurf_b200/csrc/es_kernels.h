@@ -22,6 +22,10 @@ struct ChainIO {
   float* out_sdf;   // [P]
   float* out_gc;    // [P,3]   d sdf / d x_c               (tangent mode only)
   float* out_feat;  // [P,256] geometry feature            (feat layer only)
+  // geometry feature as fp16 hi/lo plane records of the COLOUR chain's tiles (128 points): [tile][chunk 0..3][hi, lo]
+  // [16 KiB], each [k-group of 8 columns][128 rows][8 fp16] - exactly the colour chain's A-operand ring slot, so its
+  // SRC_FEAT chunks become two bulk copies instead of row-per-thread 16-byte loads of the fp32 rows
+  uint8_t* out_feat_rec;
   // colour chain
   const float* x_c;      // [P,3]
   const float* g_c;      // [P,3]
@@ -30,6 +34,7 @@ struct ChainIO {
   long long dir_div;
   long long dir_stride;
   const float* feat;     // [P,256]
+  const uint8_t* feat_rec;  // or the plane records written through out_feat_rec (feat may then be null)
   float* out_rgb;        // [P,3]
   // training planes (see LayerProg::dump): records of 16 KiB chunks, [tile][chunks per tile][16 KiB]
   uint8_t* dump_hi;          // written by this launch (forward: activation stash; reverse: zbar, the adjoints of the

@@ -656,7 +656,7 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
       // the geometry feature rows (1 KiB per point, read on demand by the SRC_FEAT chunks of layer 0 and of the skip
       // layer) of the CTA's NEXT tile go to L2 now: a whole tile of MMAs later the loads no longer wait for HBM
       const long long pn = (tile + tw.step) * TILE_ROWS + c.row;
-      if (pn < io.n_points && io.feat) {
+      if (pn < io.n_points && io.feat && !io.feat_rec) {
 #pragma unroll
         for (int blk = 0; blk < 4; ++blk) prefetch_l2(io.feat + pn * HID + 64 * blk + PCOLS * c.part);
       }
@@ -751,6 +751,11 @@ __device__ __forceinline__ void epilogue_plain(const ChainProg& prog, const Chai
           if (ck == last_prev) release_d(c, c.g - 1);
           TRACE_EPI(7000 + l * 16 + ck);  // EPI: values ready (tmem + math done)
           emit_row(row_sa, v);
+        } else if (src == SRC_FEAT && io.feat_rec) {
+          // the chunk as the geometry chain left it: two 16 KiB bulk copies straight into the ring slot
+          const uint8_t* chi = io.feat_rec + (static_cast<size_t>(tile_r) * 4 + L.arg[ck]) * (2 * CHUNK_PLANE_BYTES);
+          reload_chunk_bulk(c, slot, chi, chi + CHUNK_PLANE_BYTES);
+          continue;
         } else if (src == SRC_FEAT) {
           float v[PCOLS];
           const float4* f4 = reinterpret_cast<const float4*>(io.feat + pt * HID + col0);
@@ -1349,10 +1354,24 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
         load_frag(c.tmem + ((c.g - 1) & 1) * HID + 64 * blk, F);
         const float2 b0 = lds64f(bias_sa0 + (MAXL * HID + 64 * blk) * 4);
         const float2 b1 = lds64f(bias_sa0 + (MAXL * HID + 64 * blk) * 4 + 32);
-        if (valid) {
+        const float f0 = F.f[0][0] + b0.x, f1 = F.f[0][1] + b0.y, f2 = F.f[0][2] + b1.x, f3 = F.f[0][3] + b1.y;
+        if (valid && io.out_feat) {
           float* o = io.out_feat + pt * HID + 64 * blk + colq;
-          *reinterpret_cast<float2*>(o) = make_float2(F.f[0][0] + b0.x, F.f[0][1] + b0.y);
-          *reinterpret_cast<float2*>(o + 8) = make_float2(F.f[0][2] + b1.x, F.f[0][3] + b1.y);
+          *reinterpret_cast<float2*>(o) = make_float2(f0, f1);
+          *reinterpret_cast<float2*>(o + 8) = make_float2(f2, f3);
+        }
+        if (valid && io.out_feat_rec) {
+          // colour tile pt / 128, row pt % 128; columns (16 part + 2q, +1) sit in k-group 2 part at byte 4q, columns
+          // (16 part + 8 + 2q, +1) in k-group 2 part + 1: a warp stores 8 rows x 16 B = one full line per instruction
+          uint8_t* rec = io.out_feat_rec + (static_cast<size_t>(pt / TILE_ROWS) * 4 + blk) * (2 * CHUNK_PLANE_BYTES) +
+                         2 * c.part * A_LBO + (pt % TILE_ROWS) * 16 + 4 * q;
+          uint32_t h0, l0, h1, l1;
+          split2(f0, f1, h0, l0);
+          split2(f2, f3, h1, l1);
+          *reinterpret_cast<uint32_t*>(rec) = h0;
+          *reinterpret_cast<uint32_t*>(rec + A_LBO) = h1;
+          *reinterpret_cast<uint32_t*>(rec + CHUNK_PLANE_BYTES) = l0;
+          *reinterpret_cast<uint32_t*>(rec + CHUNK_PLANE_BYTES + A_LBO) = l1;
         }
       }
       release_d(c, c.g - 1);
