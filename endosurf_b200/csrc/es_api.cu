@@ -107,6 +107,9 @@ struct es_ctx {
   int debug_flags = 0;
   long long* trace_dev = nullptr;  // debug pipeline trace buffer (es_debug_trace)
   int trace_kind = -1;
+  int store_hint = 1;              // L2 policies (ChainIO::store_hint): plane-record stores evict_first by default -
+                                   // the 19 GB record stream of a training launch no longer evicts the packed weights
+                                   // (geometry chain 12.7 -> 11.5 ms, profiles/r2_experiments.txt)
   int feat_records = 1;            // geometry feature travels to the colour chain as fp16 plane records (0: fp32 rows)
   struct Timed {
     int kind;
@@ -884,6 +887,7 @@ static int timed_chain(es_ctx* ctx, int kind, int chain, bool tangent, const Cha
   ChainIO io2 = io;
   io2.trace = (ctx->trace_kind < 0 || ctx->trace_kind == kind) ? ctx->trace_dev : nullptr;
   io2.debug_flags = ctx->debug_flags;
+  io2.store_hint = ctx->store_hint;
   es_ctx::Timed t;
   if (int r = timer_begin(ctx, kind, io.n_points, stream, t)) return r;
   const bool pair = ctx->pair_mode && kind != K_INADJ;
@@ -1683,6 +1687,7 @@ int es_debug_set(es_ctx* ctx, int32_t key, int32_t value) {
     case 2: ctx->wgrad_sbo = value; return 0;
     case 3: ctx->scale_target = std::ldexp(1.f, value); return 0;  // adjoint scale target 2^value
     case 5: ctx->wgrad_pairs = value != 0; return 0;
+    case 8: ctx->store_hint = value; return 0;
     case 7: ctx->feat_records = value != 0; return 0;  // A/B switch of the feature plane records
     case 6: ctx->trace_kind = value; return 0;    // ES_TRACE builds: only launches of this kind write the trace (-1: all)
     case 4:  // CTA pairs on/off; the packed weights change layout: the networks must be loaded again

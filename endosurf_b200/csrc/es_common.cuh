@@ -127,6 +127,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 
+// the same with an L2 cache-policy operand (createpolicy): the packed weights are re-read by every CTA for every tile
+// and should outlive the streaming traffic of the training launches (evict_last)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive_expect_tx_sa(uint32_t bar_sa, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_sa), "r"(bytes) : "memory");
 }
@@ -142,6 +158,18 @@ __device__ __forceinline__ void tma_bulk_g2s_sa(uint32_t smem_dst_sa, const void
 // async proxy (fence.proxy.async after the generic-proxy stores, before the barrier that hands the buffer over).
 __device__ __forceinline__ void tma_bulk_s2g(void* gdst, uint32_t smem_src_sa, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src_sa), "r"(bytes)
+               : "memory");
+}
+// the same with an L2 eviction-priority hint (plane records are streamed once: evict_first keeps the packed weights and
+// the lines other kernels will re-read resident)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_bulk_s2g_hint(void* gdst, uint32_t smem_src_sa, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(smem_src_sa), "r"(bytes), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void tma_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -55,6 +55,8 @@ struct ChainIO {
   unsigned int* amax_bits;   // POST_FEAT_BAR: atomicMax of the fp32 bit pattern of |feat_bar| (next chain's scale)
   // debug: when non-null, CTA 0 records (clock64, code) pairs: trace[0] = count, then pairs (tools/trace_chain.py)
   long long* trace;
+  int store_hint;   // L2 policies, bit mask: 1 plane-record stores evict_first (every training launch), 2 the same for
+                    // forward launches only, 4 weight units evict_last
   int debug_flags;  // perf experiments only (ES_DEBUG_FLAGS): 1 = no weight copies, 2 = no A stores, 4 = no MMAs
 };
 

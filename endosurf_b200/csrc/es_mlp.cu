@@ -1481,6 +1481,8 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
       const uint32_t ubytes = static_cast<uint32_t>(prog.unit_bytes);
       const uint32_t cbytes = PAIR ? ubytes / 2 : ubytes;
       const uint8_t* src0 = prog.w_units + (PAIR ? rank * cbytes : 0);
+      const bool w_hint = (io.store_hint & 4) != 0;  // weight units with an L2 evict_last policy
+      const uint64_t w_pol = l2_policy_evict_last();
       for (long long it = 0; it < tw.n_iter; ++it) {
         for (int u = 0; u < prog.units_per_tile; u += 2) {
           const uint32_t st = wc % NSTAGE;
@@ -1491,8 +1493,14 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
           } else {
             mbar_arrive_expect_tx(full, three ? 2 * cbytes : cbytes);
             uint8_t* dst = smem + SM_W_OFF + st * STAGE_BYTES;
-            tma_bulk_g2s(dst, src0 + static_cast<size_t>(u) * ubytes, cbytes, full);
-            if (three) tma_bulk_g2s(dst + UNIT_BYTES, src0 + static_cast<size_t>(u + 1) * ubytes, cbytes, full);
+            if (w_hint) {
+              tma_bulk_g2s_hint(dst, src0 + static_cast<size_t>(u) * ubytes, cbytes, full, w_pol);
+              if (three)
+                tma_bulk_g2s_hint(dst + UNIT_BYTES, src0 + static_cast<size_t>(u + 1) * ubytes, cbytes, full, w_pol);
+            } else {
+              tma_bulk_g2s(dst, src0 + static_cast<size_t>(u) * ubytes, cbytes, full);
+              if (three) tma_bulk_g2s(dst + UNIT_BYTES, src0 + static_cast<size_t>(u + 1) * ubytes, cbytes, full);
+            }
           }
           ++wc;
         }
@@ -1640,6 +1648,12 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
     // global memory has the ring-slot layout (see LayerProg::dump).
     if (lane == 0) {
       uint32_t slot = 0, a_par = 0;
+      const bool hint = (io.store_hint & 1) || ((io.store_hint & 2) && !BWD);  // bit 1: forward (stash) launches only
+      const uint64_t pol = l2_policy_evict_first();
+      auto store = [&](uint8_t* dst, uint32_t src_sa) {
+        if (hint) tma_bulk_s2g_hint(dst, src_sa, CHUNK_PLANE_BYTES, pol);
+        else tma_bulk_s2g(dst, src_sa, CHUNK_PLANE_BYTES);
+      };
       auto handle = [&](long long tile, int idx_hi, int idx_lo) {
         mbar_wait_sa(sm + BAR_A_FULL + 8 * slot, a_par, err, 500);
         if (ES_FLAG(io, 32) && tile < tw.n_tiles) tile = blockIdx.x;  // ablation: records stay L2 resident (148 tiles)
@@ -1647,13 +1661,12 @@ mlp_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__
         bool any = false;
         if (tile < tw.n_tiles && !ES_FLAG(io, 16)) {  // (a pair's ghost tile keeps nothing)
           if (idx_hi != NO_DUMP && io.dump_hi) {
-            tma_bulk_s2g(io.dump_hi + (static_cast<size_t>(tile) * prog.n_dump + idx_hi) * CHUNK_PLANE_BYTES, slot_sa,
-                         CHUNK_PLANE_BYTES);
+            store(io.dump_hi + (static_cast<size_t>(tile) * prog.n_dump + idx_hi) * CHUNK_PLANE_BYTES, slot_sa);
             any = true;
           }
           if (idx_lo != NO_DUMP && io.dump_lo) {
-            tma_bulk_s2g(io.dump_lo + (static_cast<size_t>(tile) * prog.n_dump_lo + idx_lo) * CHUNK_PLANE_BYTES,
-                         slot_sa + SLOT_HALF_BYTES, CHUNK_PLANE_BYTES);
+            store(io.dump_lo + (static_cast<size_t>(tile) * prog.n_dump_lo + idx_lo) * CHUNK_PLANE_BYTES,
+                  slot_sa + SLOT_HALF_BYTES);
             any = true;
           }
         }

@@ -278,6 +278,8 @@ class EndoSurfRenderer(nn.Module):
                 raise _lib.EsError(f"es_create failed: {_lib.ES_E.get(rc, rc)}")
             self._ctx = ctx
             self.set_pair_mode(PAIR_MODE_DEFAULT)
+            if os.environ.get("ES_STORE_HINT"):  # A/B experiments: L2 evict_first hint on the plane-record stores
+                lib.es_debug_set(ctx, 8, int(os.environ["ES_STORE_HINT"]))
             if os.environ.get("ES_FEAT_REC"):  # A/B experiments: 0 = fp32 feature rows between the chains
                 lib.es_debug_set(ctx, 7, int(os.environ["ES_FEAT_REC"]))
             if os.environ.get("ES_DEBUG_FLAGS"):  # ablation experiments; only -DES_ABLATE builds of the library look at it
