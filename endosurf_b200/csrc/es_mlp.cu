@@ -1015,6 +1015,55 @@ __device__ __forceinline__ void load_planes_frag(const uint8_t* phi, const uint8
   else load_planes_frag_n<4>(phi, plo, H);
 }
 
+// hi-plane gate words of a fragment, raw (index 2 s + j).  They are requested before the accumulator wait / TMEM load and
+// unpacked only at their use, so that the first instruction that needs them comes after the TMEM load has been issued
+// (warp-stall sampling of the reverse SDF chain: 14 % of all samples sat on the unpack that followed the loads directly).
+__device__ __forceinline__ void fetch_gate_raw(const uint8_t* phi, int ns, uint32_t (&g)[8]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) g[j] = __ldg(reinterpret_cast<const uint32_t*>(phi + j * A_LBO));
+  if (ns == 4) {
+#pragma unroll
+    for (int s = 1; s < 4; ++s)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) g[2 * s + j] = __ldg(reinterpret_cast<const uint32_t*>(phi + j * A_LBO + s * 128));
+  }
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+// bwd_gate_frag on raw hi-plane words
+__device__ __forceinline__ void bwd_gate_frag_raw(const uint32_t (&g)[8], int act, Frag& U) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float2 h = unpack_h2(g[j]);
+      const bool m0 = h.x > 0.f, m1 = h.y > 0.f;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        U.f[s][2 * j] = m0 ? U.f[s][2 * j] : 0.f;
+        U.f[s][2 * j + 1] = m1 ? U.f[s][2 * j + 1] : 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float2 h0 = unpack_h2(g[j]), h1 = unpack_h2(g[2 + j]), h2 = unpack_h2(g[4 + j]), h3 = unpack_h2(g[6 + j]);
+      const float hp[2] = {h0.x, h0.y}, t1[2] = {h1.x, h1.y}, t2[2] = {h2.x, h2.y}, t3[2] = {h3.x, h3.y};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 2 * j + e;
+        const float ex = __expf(-100.f * hp[e]);  // 1 - sigma
+        const float sg = 1.f - ex;
+        const float ct = t1[e] * U.f[1][i] + t2[e] * U.f[2][i] + t3[e] * U.f[3][i];
+        U.f[0][i] = fmaf(100.f * ex, ct, sg * U.f[0][i]);
+        U.f[1][i] *= sg;
+        U.f[2][i] *= sg;
+        U.f[3][i] *= sg;
+      }
+    }
+  }
+}
+
 // activation backward on a fragment (see bwd_gate_plain for the formulas); everything is thread-local
 __device__ __forceinline__ void bwd_gate_frag(const Frag& H, int act, Frag& U) {
   if (act == ACT_RELU) {
@@ -1252,10 +1301,13 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
             }
             emit_frag(F, slot_sa + frag_off);
           } else {
-            Frag HG;  // gating activations first: their latency (L2, see prefetch_next_gates) overlaps the accumulator wait
+            // gating activations first (requested, not yet used): their latency (L2, see prefetch_next_gates) overlaps
+            // the accumulator wait and the TMEM load
+            Frag HG;
+            uint32_t graw[8];
             const size_t go = static_cast<size_t>(L.gate_base + blk) * CHUNK_PLANE_BYTES + frag_off;
-            load_planes_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, HG,
-                             L.bwd_act == ACT_RELU ? 1 : 4);
+            if (gate_tile_lo) load_planes_frag(gate_tile + go, gate_tile_lo + go, HG, L.bwd_act == ACT_RELU ? 1 : 4);
+            else fetch_gate_raw(gate_tile + go, L.bwd_act == ACT_RELU ? 1 : 4, graw);
             if (src == SRC_BWD_PREV) {
               if (!prev_waited) {
                 wait_d_full(c, c.g - 1);
@@ -1292,7 +1344,8 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
                 for (int i = 0; i < 4; ++i) F.f[s][i] = (a.x * w[0][i] + a.y * w[1][i] + a.z * w[2][i]) * scale;
               }
             }
-            bwd_gate_frag(HG, L.bwd_act, F);
+            if (gate_tile_lo) bwd_gate_frag(HG, L.bwd_act, F);
+            else bwd_gate_frag_raw(graw, L.bwd_act, F);
             emit_frag(F, slot_sa + frag_off);
           }
         }
@@ -1331,15 +1384,17 @@ __device__ __forceinline__ void epilogue_tangent(const ChainProg& prog, const Ch
 #pragma unroll 1
       for (int blk = 0; blk < 4; ++blk, ++c.ac) {
         Frag F, HG;
+        uint32_t graw[8];
         const size_t go = static_cast<size_t>(prog.post_gate_base + blk) * CHUNK_PLANE_BYTES + frag_off;
-        load_planes_frag(gate_tile + go, gate_tile_lo ? gate_tile_lo + go : nullptr, HG,
-                         prog.post_bwd_act == ACT_RELU ? 1 : 4);
+        if (gate_tile_lo) load_planes_frag(gate_tile + go, gate_tile_lo + go, HG, prog.post_bwd_act == ACT_RELU ? 1 : 4);
+        else fetch_gate_raw(gate_tile + go, prog.post_bwd_act == ACT_RELU ? 1 : 4, graw);
         if (!waited) {
           wait_d_full(c, c.g - 1);
           waited = true;
         }
         load_frag(c.tmem + ((c.g - 1) & 1) * HID + 64 * blk, F);
-        bwd_gate_frag(HG, prog.post_bwd_act, F);
+        if (gate_tile_lo) bwd_gate_frag(HG, prog.post_bwd_act, F);
+        else bwd_gate_frag_raw(graw, prog.post_bwd_act, F);
         const uint32_t slot = claim_slot<true>(c, blk);
         emit_frag(F, c.sm + SM_A_OFF + slot * SLOT_BYTES + frag_off);
         publish_chunk(c, slot, 950 + blk);
