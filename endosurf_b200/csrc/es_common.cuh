@@ -47,6 +47,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Slow path of mbar_wait, kept out of line so that the hot loops only carry the try_wait + branch.  Returns false if
 // the watchdog tripped (the caller keeps going; results are garbage and the error word tells the host).  `err` points
 // to a global int; `code` identifies the wait site.
+#ifndef ES_WAIT_BACKOFF_NS
+#define ES_WAIT_BACKOFF_NS 128
+#endif
 static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar_sa, uint32_t parity, int* err, int code) {
   uint32_t spins = 0;
   for (;;) {
@@ -64,6 +67,14 @@ static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar_sa, uint32_t par
       return false;
     }
     if ((spins & 0xFFFF) == 0 && *reinterpret_cast<volatile int*>(err) != 0) return false;
+#if ES_WAIT_BACKOFF_NS > 0
+    // Waits that are long by construction (the epilogue waiting for an accumulator or a free ring slot, the weight
+    // producer and the record warp waiting for the MMAs) back off between polls: a polling warp costs ~6 issue slots per
+    // iteration on a sub-partition it shares with the MMA issuer and the working epilogue warps (source-level ncu:
+    // 12-13 % of the executed instructions of a chain were barrier polls).  The MMA issuer's own waits (codes 3xx) and
+    // the pair relay (41x, 42x) stay tight.
+    if (code < 300 || code == 400 || code == 401 || code == 500) asm volatile("nanosleep.u32 %0;" ::"n"(ES_WAIT_BACKOFF_NS));
+#endif
   }
 }
 __device__ __forceinline__ bool mbar_wait_sa(uint32_t bar_sa, uint32_t parity, int* err, int code) {
