@@ -232,6 +232,58 @@ def reference_rays_per_s(n_rays, steps, warmup, device, mode="train", threads=No
     return n_rays / t, t, kind
 
 
+def reference_latency_ms(mode, device, chunk=2048, net_chunk=80000, hw=HW, res=256):
+    """BASELINE.md run B2: the UNMODIFIED reference on `device` (stock PyTorch, fp32, TF32 off) doing what our latency
+    modes do - `frame`: one full 512x512 frame through its renderer in `chunk`-ray chunks with colour / depth / normal
+    of every chunk converted to host numpy (trainer_endosurf.py:228-240); `grid256`: its own extract_fields over the
+    256^3 grid with run_fn_split at `net_chunk` (utils.py:139-157, endosurf.py:493-494).  One warm-up chunk / 128^3
+    block, then ONE timed pass (a frame takes ~18 s there)."""
+    import importlib
+    from oracle import ref_shims  # baseline infrastructure only
+    if not ref_shims.available():
+        raise RuntimeError("oracle/_ref has not been built")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    mod = ref_shims.load_reference()
+    r = mod.EndoSurfRenderer(copy.deepcopy(RENDER_CFG), copy.deepcopy(NET_CFG), device)
+    seeded_state(r.model)
+    r.eval()
+
+    def sync():
+        if device != "cpu":
+            torch.cuda.synchronize()
+    if mode == "frame":
+        rays_all = make_rays(0, frame=7, hw=hw, all_pixels=True).to(device)
+
+        def run(n_rays):
+            out = []
+            for rs in rays_all[:n_rays].split(chunk):
+                o = r(rs, iter_step=ITER_STEP)
+                nrm = (o["gradients_o"] * o["weights"][:, :128, None]).sum(dim=1)
+                out.append([x.detach().cpu().numpy() for x in (o["color_map"], o["depth_map"], nrm)])
+                del o
+            return out
+        run(chunk)
+        sync()
+        t0 = time.perf_counter()
+        run(hw * hw)
+        sync()
+        return (time.perf_counter() - t0) * 1e3
+    ut = importlib.import_module("src.renderer.utils")
+    t = torch.tensor([0.5], device=device)
+
+    def query(pts):
+        return ut.run_fn_split(lambda p: r.model.get_sdf_from_observed_space(p, t), pts, net_chunk, cpu=True)
+    ut.extract_fields([-1.0] * 3, [1.0] * 3, min(64, res), query, device)
+    sync()
+    t0 = time.perf_counter()
+    u = ut.extract_fields([-1.0] * 3, [1.0] * 3, res, query, device)
+    sync()
+    assert u.shape == (res, res, res)
+    return (time.perf_counter() - t0) * 1e3
+
+
 def reference_sample_rays(steps, warmup):
     """Bounded CPU sample: about 12k rays of CPU work in total (2-3 minutes on a 16-core host), <= 1024 rays per step
     (the reference keeps every chunk's autograd graph: 4096 rays x 128 samples do not fit a host's memory budget)."""
@@ -539,6 +591,22 @@ def run_latency(args, r, dev, world, rank):
                                   "traffic": None, "algorithmic_flops_per_launch": fl,
                                   "note": "33.69 TFLOP per grid (SURVEY 8d); sdf-query chain, 3 fp16 MMAs per product"},
                      "gpu_launches": int(r.launch_count()), "sdf_range": [float(u_host.min()), float(u_host.max())]})
+    if not args.no_gpu_reference:
+        r.release_workspace()
+        torch.cuda.empty_cache()
+        try:
+            ref_ms = reference_latency_ms(args.mode, f"cuda:{dev.index or 0}")
+            line["gpu_reference"] = {
+                "value": ref_ms, "unit": line["unit"], "kind": "reference",
+                "what": "the unmodified reference (oracle/_ref) on the same GPU, stock PyTorch "
+                        f"{torch.__version__} ops, fp32, TF32 off, one timed pass after a warm-up chunk: " +
+                        ("its renderer over the same 512x512 frame in 2048-ray chunks, per-chunk colour / depth / normal "
+                         "to host numpy (trainer_endosurf.py:228-240)" if args.mode == "frame" else
+                         "its extract_fields over the 256^3 grid, run_fn_split at net_chunk 80000, blocks to host numpy "
+                         "(utils.py:139-157)"),
+                "speedup_value": ref_ms / line["value"], "speedup_e2e": ref_ms / line["e2e"]["value"]}
+        except Exception as e:  # never lose the main line to the baseline
+            line["gpu_reference"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
