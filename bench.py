@@ -162,16 +162,22 @@ def measured_peaks():
     return 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)", 6500.0
 
 
-def ncu_traffic(mode):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel at this workload's size, read
-    from the committed ncu capture summary (profiles/r2_ncu_traffic.json, written by tools/ncu_traffic.py from the
-    `ncu --set full` report); null when no capture of the current kernels has been committed."""
+def ncu_capture(mode, key="dram_bytes_per_launch"):
+    """One figure of the committed `ncu --set full` capture of the roofline kernel at this workload's size
+    (profiles/r2_ncu_traffic.json, extracted from profiles/r2_ncu_summary.txt): `dram_bytes_per_launch` =
+    dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, `tensor_pipe_pct` =
+    sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed; null when no capture has been committed."""
     p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(mode, {}).get("dram_bytes_per_launch")
+            v = json.load(f).get(mode, {}).get(key)
+        return None if v is None else float(v)
     except Exception:
         return None
+
+
+def ncu_traffic(mode):
+    return ncu_capture(mode, "dram_bytes_per_launch")
 
 
 # ------------------------------------------------------------------------------------------------ the reference itself
@@ -471,6 +477,7 @@ def run_ours(args):
                                    "point" + ("; training variant keeping the plane records" if train else "") + ")",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": ncu_traffic(mode),
+                         "tensor_pipe_pct_ncu": ncu_capture(mode, "tensor_pipe_pct"),
                          "algorithmic_flops_per_launch": alg_flops_launch, "points_per_launch": pts_per_launch,
                          "ms_per_launch": ms_launch,
                          "note": f"algorithmic = 2*(4D+2S) FLOP/point (SURVEY 8d); the kernel issues {terms_note} "
