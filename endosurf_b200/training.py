@@ -19,6 +19,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import List, Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -34,46 +35,75 @@ def net_ids(renderer) -> List[int]:
 
 def param_list(renderer) -> List[torch.Tensor]:
     """[bias, weight_g, weight_v] per layer per network, in ``module.parameters()`` order (without ``variance``)."""
-    m = renderer.model
-    nets = ([m.deform_network] if m.use_deform else []) + [m.sdf_network, m.color_network]
-    out = []
-    for net in nets:
-        for lyr in net.net:
-            out += [lyr.bias, lyr.weight_g, lyr.weight_v]
-    return out
+    return renderer._fast_params()[:-1]
+
+
+class _StaticTables:
+    """The part of es_train_params that only depends on WHERE the parameters live: the weight_v / weight_g pointer
+    tables, the layout of the flat gradient buffer and the ctypes arrays the gradient pointers are written into.
+    Built once per renderer (re-built when a parameter moves) instead of once per backward call: 3 backward calls per
+    trainer step (render, errorondepth, surface_neighbour_error) used to spend about 1 ms of host time here each."""
+
+    def __init__(self, renderer, params: Tuple[torch.Tensor, ...]):
+        L = renderer._cfg_struct.n_layers
+        self.sizes = [p.numel() for p in params]
+        self.shapes = [p.shape for p in params]
+        self.total = sum(self.sizes)
+        offs, off = [], 0
+        self.view_args = []  # (shape, contiguous strides, element offset) of every gradient inside the flat buffer
+        for p, n in zip(params, self.sizes):
+            offs.append(4 * off)
+            self.view_args.append((tuple(p.shape), tuple(torch.empty(0).new_empty(p.shape).stride()) if p.dim() > 2
+                                   else ((p.shape[1], 1) if p.dim() == 2 else ((1,) if p.dim() == 1 else ())), off))
+            off += n
+        names = ("v", "g", "grad_v", "grad_g", "grad_b")
+        fields = {k: [None, None, None] for k in names}
+        self.keep = []
+        self.grad_tables = []  # (ctypes array of L pointers, int64 byte offsets of its L gradients in the flat buffer)
+        k = 0
+        for net in net_ids(renderer):
+            tabs = {n: (C.c_void_p * L)() for n in names}
+            goff = {n: np.zeros(L, dtype=np.int64) for n in ("grad_b", "grad_g", "grad_v")}
+            for l in range(L):
+                g, v = params[k + 1], params[k + 2]  # (bias, weight_g, weight_v)
+                tabs["v"][l], tabs["g"][l] = v.data_ptr(), g.data_ptr()
+                goff["grad_b"][l], goff["grad_g"][l], goff["grad_v"][l] = offs[k], offs[k + 1], offs[k + 2]
+                k += 3
+            for n in names:
+                fields[n][net] = C.cast(tabs[n], C.POINTER(C.c_void_p))
+                self.keep.append(tabs[n])
+            self.grad_tables += [(tabs[n], goff[n]) for n in goff]
+        self.struct = _lib.EsTrainParams(**{n: (C.POINTER(C.c_void_p) * 3)(*[q if q is not None else C.POINTER(C.c_void_p)()
+                                                                           for q in fields[n]]) for n in names})
 
 
 class _ParamTables:
     """ctypes view (es_train_params) of the parameters and freshly allocated gradient tensors."""
 
     def __init__(self, renderer, params: Tuple[torch.Tensor, ...]):
-        L = renderer._cfg_struct.n_layers
-        self.grads = []
-        self.keep = []
-        fields = {k: [None, None, None] for k in ("v", "g", "grad_v", "grad_g", "grad_b")}
+        key = tuple([p.data_ptr() for p in params])
+        cached = renderer.__dict__.get("_ptab_static")
+        if cached is None or cached[0] != key:
+            cached = (key, _StaticTables(renderer, params))
+            renderer.__dict__["_ptab_static"] = cached
+        st = cached[1]
         # ONE zero-filled buffer for all gradients in parameter order (one fill launch; the bias gradients are
-        # accumulated by the kernels), handed out as views
-        self.flat = torch.zeros(sum(p.numel() for p in params), device=params[0].device, dtype=torch.float32)
-        off = 0
-        views = []
-        for p in params:
-            views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
-        k = 0
-        for net in net_ids(renderer):
-            tabs = {n: (C.c_void_p * L)() for n in fields}
-            for l in range(L):
-                b, g, v = params[k], params[k + 1], params[k + 2]
-                gb, gg, gv = views[k], views[k + 1], views[k + 2]
-                k += 3
-                self.grads += [gb, gg, gv]
-                tabs["v"][l], tabs["g"][l] = v.data_ptr(), g.data_ptr()
-                tabs["grad_v"][l], tabs["grad_g"][l], tabs["grad_b"][l] = gv.data_ptr(), gg.data_ptr(), gb.data_ptr()
-            for n in fields:
-                fields[n][net] = C.cast(tabs[n], C.POINTER(C.c_void_p))
-                self.keep.append(tabs[n])
-        self.struct = _lib.EsTrainParams(**{n: (C.POINTER(C.c_void_p) * 3)(*[p if p is not None else C.POINTER(C.c_void_p)()
-                                                                           for p in fields[n]]) for n in fields})
+        # accumulated by the kernels), handed out as views.  The library reads the pointer tables on the host while
+        # the call is being enqueued, so the (cached) ctypes arrays can be re-pointed for every backward call.
+        self.flat = torch.zeros(st.total, device=params[0].device, dtype=torch.float32)
+        self._st = st
+        base = self.flat.data_ptr()
+        for arr, off in st.grad_tables:
+            ptrs = off + base
+            C.memmove(arr, ptrs.ctypes.data, ptrs.nbytes)
+        self.struct = st.struct
+
+    @property
+    def grads(self) -> List[torch.Tensor]:
+        """The gradients as per-parameter views of the flat buffer (only built when autograd needs them: a bound
+        gradient sink takes the flat buffer)."""
+        flat = self.flat
+        return [flat.as_strided(shp, std, off) for shp, std, off in self._st.view_args]
 
 
 def _deliver(renderer, params, tabs, extra):
@@ -85,12 +115,6 @@ def _deliver(renderer, params, tabs, extra):
     if sink is not None and sink.accumulate(params, tabs.flat, extra):
         return [None] * len(extra), [None] * len(params)
     return [g for _, g in extra], list(tabs.grads)
-
-
-def _check_params(params):
-    for p in params:
-        if not p.is_contiguous() or p.dtype != torch.float32:
-            raise ValueError("endosurf_b200 parameters must be contiguous fp32 tensors")
 
 
 def _stash(renderer, n: int, dev) -> torch.Tensor:
@@ -113,7 +137,6 @@ class RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, renderer, rays, z, cos_ratio, variance, *params):
         lib, ectx = _lib.load(), renderer._context()
-        _check_params(params)
         renderer._sync_weights()
         dev = rays.device
         R, M = z.shape
@@ -180,7 +203,6 @@ class PointFieldFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, renderer, x, d, t, *params):
         lib, ectx = _lib.load(), renderer._context()
-        _check_params(params)
         renderer._sync_weights()
         dev = x.device
         n = x.shape[0]

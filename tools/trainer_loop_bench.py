@@ -90,6 +90,8 @@ def main():
     ap.add_argument("--hw", type=int, default=512)
     ap.add_argument("--kinds", default="fp16x3,fp16x1,reference")
     args = ap.parse_args()
+    json_out = os.fdopen(os.dup(1), "w")  # the reference trainer prints banners on stdout: they go to stderr
+    os.dup2(2, 1)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     work = tempfile.mkdtemp(prefix="es_loop_")
@@ -131,7 +133,7 @@ def main():
         for k in res:
             if k != "reference":
                 res[k]["speedup_vs_reference_renderer"] = res[k]["rays_per_s"] / res["reference"]["rays_per_s"]
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
 
 
 if __name__ == "__main__":
