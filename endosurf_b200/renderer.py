@@ -362,8 +362,9 @@ class EndoSurfRenderer(nn.Module):
     def point_field(self, x, d, t):
         """Differentiable EndoSurfNet.forward + gradient queries on explicit points:
         (sdf [n,1], g_c [n,3], jac [n,3,3], rgb [n,3]); gradients flow to every network parameter."""
-        from .training import PointFieldFn, param_list
-        return PointFieldFn.apply(self, x, d, t, *param_list(self))
+        from .training import PointFieldFn, param_hub
+        params, hub = param_hub(self)
+        return PointFieldFn.apply(self, x, d, t, hub, params)
 
     def _sample_z(self, rays, iter_step, perturb_overwrite):
         """Coarse + hierarchical sampling only (no grad, CUDA): z_vals [R,M]."""
@@ -398,24 +399,24 @@ class EndoSurfRenderer(nn.Module):
         """render_rays with autograd (endosurf.py:60-213): sampling runs without grad exactly as in the reference
         (:86); everything after it - points, the three MLPs with normals and Jacobian, compositing - is one fused
         library forward and one library backward (training.RenderFn)."""
-        from .training import RenderFn, param_list
+        from .training import RenderFn, param_hub
         rays = rays.detach().contiguous().float()
         R = rays.shape[0]
         with torch.no_grad():
             z = z_vals_override.detach().contiguous().float() if z_vals_override is not None else \
                 self._sample_z(rays, iter_step, perturb_overwrite)
         cos_ratio = self.get_cos_anneal_ratio(iter_step) if cos_ratio is None else float(cos_ratio)
-        params = param_list(self)
+        params, hub = param_hub(self)
         variance = self.model.deviation_network.variance
         names = ["color_map", "depth_map", "gradients_o", "gradient_o_error", "weights", "cdf", "sdf",
                  "sampled_color", "weight_max", "s_val", "eikonal_den"]
         if R <= self.train_ray_chunk:
-            vals = RenderFn.apply(self, rays, z, cos_ratio, variance, *params)
+            vals = RenderFn.apply(self, rays, z, cos_ratio, variance, hub, params)
             out = dict(zip(names, vals))
         else:
             # very large batches: several library calls; the eikonal mean is re-normalised over the whole batch
             parts = [RenderFn.apply(self, rays[r0:r0 + self.train_ray_chunk], z[r0:r0 + self.train_ray_chunk],
-                                    cos_ratio, variance, *params) for r0 in range(0, R, self.train_ray_chunk)]
+                                    cos_ratio, variance, hub, params) for r0 in range(0, R, self.train_ray_chunk)]
             out = {k: torch.cat([p[i] for p in parts]) for i, k in enumerate(names)
                    if k not in ("gradient_o_error", "eikonal_den")}
             dens = torch.stack([p[10].reshape(()) for p in parts])           # sum(relax) + 1e-6 of every chunk

@@ -77,16 +77,60 @@ class _StaticTables:
                                                                            for q in fields[n]]) for n in names})
 
 
+def _static_tables(renderer, params) -> _StaticTables:
+    key = tuple([p.data_ptr() for p in params])
+    cached = renderer.__dict__.get("_ptab_static")
+    if cached is None or cached[0] != key:
+        cached = (key, _StaticTables(renderer, params))
+        renderer.__dict__["_ptab_static"] = cached
+    return cached[1]
+
+
+class ParamHubFn(torch.autograd.Function):
+    """(params...) -> handle [total]: a tensor whose only purpose is its autograd edge.
+
+    The library's backward calls produce ALL parameter gradients as one flat buffer.  A trainer step has three such
+    calls (render_rays, errorondepth, surface_neighbour_error); handing 81 views per call to autograd made it add them
+    pairwise - 164 tiny launches per step.  Instead every call takes this handle as its one differentiable
+    "parameter" input and returns the flat buffer as the handle's gradient: autograd sums the flat buffers (2 adds) and
+    this node hands the 81 per-parameter views of the sum to the parameters once."""
+
+    @staticmethod
+    def forward(ctx, renderer, *params):
+        st = _static_tables(renderer, params)
+        ctx.view_args = st.view_args
+        ctx.set_materialize_grads(False)  # a bound gradient sink leaves nothing to route: no zero-filled stand-in
+        return torch.empty(st.total, device=params[0].device, dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, flat):
+        if flat is None:
+            return (None,) * (1 + len(ctx.view_args))
+        flat = flat.contiguous()
+        base = flat.storage_offset()
+        return (None, *[flat.as_strided(shp, std, base + off) for shp, std, off in ctx.view_args])
+
+
+def param_hub(renderer):
+    """-> (params, handle): the network parameters ([bias, weight_g, weight_v] per layer per network) and the hub handle
+    that stands for them in the autograd graph.  The hub node only routes gradients to parameter OBJECTS, so it is kept
+    across calls and iterations until a parameter object, its requires_grad flag or its device changes."""
+    params = tuple(renderer._fast_params()[:-1])
+    key = (tuple([id(p) for p in params]), tuple([p.requires_grad for p in params]), params[0].device)
+    cached = renderer.__dict__.get("_hub")
+    if cached is None or cached[0] != key or not cached[2].requires_grad or not torch.is_grad_enabled():
+        handle = ParamHubFn.apply(renderer, *params)
+        cached = (key, params, handle)  # the parameters are kept alive with the key: their ids stay valid
+        if handle.requires_grad:
+            renderer.__dict__["_hub"] = cached
+    return cached[1], cached[2]
+
+
 class _ParamTables:
     """ctypes view (es_train_params) of the parameters and freshly allocated gradient tensors."""
 
     def __init__(self, renderer, params: Tuple[torch.Tensor, ...]):
-        key = tuple([p.data_ptr() for p in params])
-        cached = renderer.__dict__.get("_ptab_static")
-        if cached is None or cached[0] != key:
-            cached = (key, _StaticTables(renderer, params))
-            renderer.__dict__["_ptab_static"] = cached
-        st = cached[1]
+        st = _static_tables(renderer, params)
         # ONE zero-filled buffer for all gradients in parameter order (one fill launch; the bias gradients are
         # accumulated by the kernels), handed out as views.  The library reads the pointer tables on the host while
         # the call is being enqueued, so the (cached) ctypes arrays can be re-pointed for every backward call.
@@ -107,14 +151,14 @@ class _ParamTables:
 
 
 def _deliver(renderer, params, tabs, extra):
-    """Hand the gradients of a backward call to autograd - or, when a gradient sink is bound to the renderer
-    (``distributed.FlatGradBucket.bind``: every ``p.grad`` is a view into one flat buffer laid out in exactly this
-    parameter order), add them there with ONE launch and return ``None`` for them, instead of the 80+ per-parameter
-    accumulation launches autograd would issue.  ``extra`` = [(parameter, gradient)] delivered the same way."""
+    """Hand the gradients of a backward call to autograd as ONE flat tensor (the gradient of the hub handle,
+    :class:`ParamHubFn`) - or, when a gradient sink is bound to the renderer (``distributed.FlatGradBucket.bind``: every
+    ``p.grad`` is a view into one flat buffer laid out in exactly this parameter order), add them there with ONE launch
+    and return ``None``.  ``extra`` = [(parameter, gradient)] delivered the same way.  -> (extra gradients, flat)"""
     sink = getattr(renderer, "_grad_sink", None)
     if sink is not None and sink.accumulate(params, tabs.flat, extra):
-        return [None] * len(extra), [None] * len(params)
-    return [g for _, g in extra], list(tabs.grads)
+        return [None] * len(extra), None
+    return [g for _, g in extra], tabs.flat
 
 
 def _stash(renderer, n: int, dev) -> torch.Tensor:
@@ -129,13 +173,15 @@ def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 class RenderFn(torch.autograd.Function):
-    """(rays [R,9], z_vals [R,M], variance, params...) -> (color_map, depth_map, gradients_o, gradient_o_error,
+    """(rays [R,9], z_vals [R,M], variance, hub handle, params) -> (color_map, depth_map, gradients_o, gradient_o_error,
     weights, cdf, sdf, sampled_color, weight_max, s_val, eikonal_den); the last three are not differentiable here (the
     reference only logs weight_max / s_val; eikonal_den = sum(relax) + 1e-6 is what data-parallel training needs to
     re-normalise the eikonal mean over all ranks)."""
 
     @staticmethod
-    def forward(ctx, renderer, rays, z, cos_ratio, variance, *params):
+    def forward(ctx, renderer, rays, z, cos_ratio, variance, hub, params):
+        """hub: the handle of :func:`param_hub` (its gradient is the flat parameter-gradient buffer); params: the
+        parameter tuple it stands for (opaque to autograd)."""
         lib, ectx = _lib.load(), renderer._context()
         renderer._sync_weights()
         dev = rays.device
@@ -193,15 +239,15 @@ class RenderFn(torch.autograd.Function):
                                           _ptr(var_grad), renderer._stream())
         _lib.check(ectx, rc, "es_render_train_backward")
         renderer._poll_device_error()
-        (vg,), grads = _deliver(renderer, ctx.params, tabs, [(variance, var_grad.reshape(variance.shape))])
-        return (None, None, None, None, vg, *grads)
+        (vg,), flat = _deliver(renderer, ctx.params, tabs, [(variance, var_grad.reshape(variance.shape))])
+        return (None, None, None, None, vg, flat, None)
 
 
 class PointFieldFn(torch.autograd.Function):
-    """(x [n,3], d [n,3], t [n,1], params...) -> (sdf [n,1], g_c [n,3], jac [n,3,3], rgb [n,3])."""
+    """(x [n,3], d [n,3], t [n,1], hub handle, params) -> (sdf [n,1], g_c [n,3], jac [n,3,3], rgb [n,3])."""
 
     @staticmethod
-    def forward(ctx, renderer, x, d, t, *params):
+    def forward(ctx, renderer, x, d, t, hub, params):
         lib, ectx = _lib.load(), renderer._context()
         renderer._sync_weights()
         dev = x.device
@@ -242,5 +288,5 @@ class PointFieldFn(torch.autograd.Function):
                                          C.byref(tabs.struct), renderer._stream())
         _lib.check(ectx, rc, "es_point_train_backward")
         renderer._poll_device_error()
-        _, grads = _deliver(renderer, ctx.params, tabs, [])
-        return (None, None, None, None, *grads)
+        _, flat = _deliver(renderer, ctx.params, tabs, [])
+        return (None, None, None, None, flat, None)

@@ -84,3 +84,91 @@ def test_fast_param_traversal_and_gradient_tables():
             for i, x in enumerate(g):
                 x.fill_(i + 1.0)
             assert bool((t.flat != 0).all())  # the views tile the buffer
+
+
+def test_param_hub_routes_flat_gradients(monkeypatch):
+    """Autograd plumbing of the training path without a GPU: the library is replaced by a stand-in (every entry point
+    returns 0) and the backward's flat gradient buffer by a known pattern.  Two library backward calls in one graph
+    (render_rays + a point-field loss, as the reference's train_step has) must deliver pattern x 2 to every parameter
+    through ONE flat addition + the hub node; a bound gradient sink must end up with the same numbers without the hub
+    node running; the hub handle is reused until a parameter's requires_grad flag changes."""
+    import collections
+    import copy
+    import ctypes
+    from torch.utils._python_dispatch import TorchDispatchMode
+    from endosurf_b200 import EndoSurfRenderer, _lib, renderer as rmod, training, distributed as dp
+
+    class Fake:
+        def __getattr__(self, name):
+            def fn(*a):
+                if name == "es_train_stash_bytes":
+                    a[2]._obj.value = 64
+                return 0
+            return fn
+
+    fake = Fake()
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+    monkeypatch.setattr(rmod.EndoSurfRenderer, "_context", lambda self: ctypes.c_void_p(1))
+    monkeypatch.setattr(rmod.EndoSurfRenderer, "_stream", lambda self: ctypes.c_void_p(0))
+    orig_init = training._ParamTables.__init__
+
+    def init(self, renderer, params):
+        orig_init(self, renderer, params)
+        self.flat.copy_(torch.arange(self.flat.numel(), dtype=torch.float32) % 7)
+    monkeypatch.setattr(training._ParamTables, "__init__", init)
+
+    cfg = load_cfg()
+    rc = copy.deepcopy(cfg["render"])
+    rc.update(n_samples=8, n_importance=8)
+    r = EndoSurfRenderer(rc, cfg["net"], device="cpu")
+    r.train()
+    rays = torch.rand(16, 9)
+    x, d, t = torch.rand(10, 3) - 0.5, torch.nn.functional.normalize(torch.randn(10, 3), dim=-1), torch.rand(10, 1)
+    params = [p for v in r.get_train_params().values() for p in v]
+    n_net = sum(p.numel() for p in params[:-1])
+    pat = torch.arange(n_net, dtype=torch.float32) % 7
+
+    class Count(TorchDispatchMode):
+        def __init__(self):
+            super().__init__()
+            self.c = collections.Counter()
+
+        def __torch_dispatch__(self, func, types, args=(), kwargs=None):
+            self.c[func.__name__] += 1
+            return func(*args, **(kwargs or {}))
+
+    def backward_twice():
+        o = r.render_rays(rays, iter_step=1000)
+        sdf = r.point_field(x, d, t)[0]
+        with Count() as c:
+            torch.autograd.backward([o["color_map"], sdf], [torch.ones_like(o["color_map"]), torch.ones_like(sdf)])
+        return c.c
+
+    # (1) plain autograd: p.grad of every network parameter = 2 x pattern, with one flat add instead of 81 x 2
+    ops = backward_twice()
+    assert torch.equal(torch.cat([p.grad.reshape(-1) for p in params[:-1]]), 2 * pat)
+    assert all(p.grad.shape == p.shape for p in params)
+    assert ops["add.Tensor"] == 1 and ops["as_strided.default"] == 81, dict(ops)
+    # (2) flat bucket, unbound and bound: identical numbers; bound = 2 flat additions and no per-parameter work
+    bucket = dp.FlatGradBucket(params)
+    res = {}
+    for bound in (False, True):
+        r._grad_sink = bucket if bound else None
+        bucket.zero()
+        ops = backward_twice()
+        res[bound] = bucket.flat[:n_net].clone()
+        if bound:
+            assert ops["as_strided.default"] == 0 and ops["add_.Tensor"] <= 4, dict(ops)
+    r._grad_sink = None
+    assert torch.equal(res[False], res[True]) and torch.equal(res[True], 2 * pat)
+    # (3) the hub handle lives across calls; a requires_grad change or no-grad mode gives a new one
+    h1 = training.param_hub(r)[1]
+    assert training.param_hub(r)[1] is h1
+    params[3].requires_grad_(False)
+    assert training.param_hub(r)[1] is not h1
+    params[3].requires_grad_(True)
+    with torch.no_grad():
+        assert not training.param_hub(r)[1].requires_grad
+    assert training.param_hub(r)[1].requires_grad
+    (g,) = torch.autograd.grad(r.point_field(x, d, t)[0].sum(), [params[2]])
+    assert g.shape == params[2].shape
