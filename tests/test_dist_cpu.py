@@ -89,6 +89,53 @@ def test_data_parallel_step_equals_single_process_on_the_union_batch():
     assert not torch.allclose(sum(g_avg) / world, ref, rtol=1e-3, atol=1e-6)
 
 
+def _renderer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import copy
+    import fake_lib
+    from conftest import load_cfg
+    from endosurf_b200 import EndoSurfRenderer, distributed as dp
+    fake_lib.install()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = load_cfg()
+    rc = copy.deepcopy(cfg["render"])
+    rc.update(n_samples=8, n_importance=8)
+    torch.manual_seed(0)
+    r = EndoSurfRenderer(rc, cfg["net"], device="cpu")
+    r.train()
+    params = [p for v in r.get_train_params().values() for p in v]
+    bucket = dp.FlatGradBucket(params).bind(r)
+    g = torch.Generator().manual_seed(3)
+    rays, cgt, dgt = torch.rand(16, 9, generator=g), torch.rand(16, 3, generator=g), torch.rand(16, 1, generator=g)
+    msk = (torch.rand(16, 1, generator=g) < 0.6).float()
+    sl = dp.shard_rays(16, world, rank)
+    o = r(rays[sl], iter_step=1000)
+    terms, eps = dp.render_loss_terms(r, o, cgt[sl], dgt[sl], msk[sl], msk[sl])
+    # (the stand-in library leaves the outputs uninitialised: the loss VALUE is garbage, its graph is what is tested)
+    dp.dp_backward(bucket, terms, eps)
+    n_net = sum(p.numel() for p in params[:-1])
+    out[rank] = (bucket.flat[:n_net].clone(), all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views)))
+    dist.destroy_process_group()
+
+
+def test_renderer_gradient_sink_under_data_parallel():
+    """The renderer's own host path at world size 2 (stand-in library, tests/fake_lib.py): each rank's library backward
+    adds its flat gradient (a known pattern) into the bound bucket, the parameter hub stays out of the way, ONE
+    all-reduce leaves world x pattern on every rank, and p.grad are still the bucket's views."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fake_lib
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_renderer_worker, args=(world, port, out), nprocs=world, join=True)
+    for rk in range(world):
+        flat, views_ok = out[rk]
+        assert views_ok
+        assert torch.equal(flat, world * fake_lib.pattern(flat.numel())), f"rank {rk}"
+
+
 def test_bench_shards_rays_per_rank():
     sys.path.insert(0, ROOT)
     import bench

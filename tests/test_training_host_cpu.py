@@ -94,28 +94,10 @@ def test_param_hub_routes_flat_gradients(monkeypatch):
     node running; the hub handle is reused until a parameter's requires_grad flag changes."""
     import collections
     import copy
-    import ctypes
     from torch.utils._python_dispatch import TorchDispatchMode
-    from endosurf_b200 import EndoSurfRenderer, _lib, renderer as rmod, training, distributed as dp
-
-    class Fake:
-        def __getattr__(self, name):
-            def fn(*a):
-                if name == "es_train_stash_bytes":
-                    a[2]._obj.value = 64
-                return 0
-            return fn
-
-    fake = Fake()
-    monkeypatch.setattr(_lib, "load", lambda: fake)
-    monkeypatch.setattr(rmod.EndoSurfRenderer, "_context", lambda self: ctypes.c_void_p(1))
-    monkeypatch.setattr(rmod.EndoSurfRenderer, "_stream", lambda self: ctypes.c_void_p(0))
-    orig_init = training._ParamTables.__init__
-
-    def init(self, renderer, params):
-        orig_init(self, renderer, params)
-        self.flat.copy_(torch.arange(self.flat.numel(), dtype=torch.float32) % 7)
-    monkeypatch.setattr(training._ParamTables, "__init__", init)
+    import fake_lib
+    from endosurf_b200 import EndoSurfRenderer, training, distributed as dp
+    fake_lib.install(monkeypatch.setattr)
 
     cfg = load_cfg()
     rc = copy.deepcopy(cfg["render"])
@@ -126,7 +108,7 @@ def test_param_hub_routes_flat_gradients(monkeypatch):
     x, d, t = torch.rand(10, 3) - 0.5, torch.nn.functional.normalize(torch.randn(10, 3), dim=-1), torch.rand(10, 1)
     params = [p for v in r.get_train_params().values() for p in v]
     n_net = sum(p.numel() for p in params[:-1])
-    pat = torch.arange(n_net, dtype=torch.float32) % 7
+    pat = fake_lib.pattern(n_net)
 
     class Count(TorchDispatchMode):
         def __init__(self):
