@@ -152,3 +152,23 @@ def test_reference_arm_is_rank0_only(monkeypatch, capsys):
         steps, warmup, ref_rays, rays, gpus, mode, precision_terms = 1, 1, 2, 4096, 2, "forward", 3
     bench.run_reference(A)
     assert capsys.readouterr().out == ""
+
+
+def test_shard_rays_partitions_any_batch():
+    """Ragged and empty cases of the ray partition: for every batch size and world size the shards are
+    contiguous, disjoint, in rank order and cover the batch exactly; surplus ranks get empty shards."""
+    sys.path.insert(0, ROOT)
+    from endosurf_b200 import distributed as dp
+    for world in range(1, 9):
+        for n in list(range(0, 40)) + [4096, 65536, 65537]:
+            shards = [dp.shard_rays(n, world, r) for r in range(world)]
+            covered = []
+            for sl in shards:
+                assert 0 <= sl.start <= sl.stop <= n
+                covered += list(range(sl.start, sl.stop)) if n < 100 else []
+            assert shards[0].start == 0 and shards[-1].stop == n
+            assert all(a.stop == b.start for a, b in zip(shards, shards[1:]))
+            if n < 100:
+                assert covered == list(range(n))
+            sizes = [sl.stop - sl.start for sl in shards]
+            assert max(sizes) == (n + world - 1) // world
